@@ -1,0 +1,38 @@
+"""Reference arm of bench.py: run the UNMODIFIED reference (Microsoft/multiverso) installed under
+``baseline/_ref`` through its own CLI (Applications/WordEmbedding) on the same metric/config.
+
+The reference is a CMake/MPI C++ project: ``pip install /root/reference`` cannot work (there
+is no setup.py / pyproject at its root) and CMake needs ``find_package(MPI REQUIRED)``
+(CMakeLists.txt:11) while the image has no MPI.  See DESIGN.md "Reference arm" for the recorded
+outcome.  ``tools/build_reference.sh`` attempts an out-of-tree build of the unmodified sources
+against a tiny single-node MPI shim (the reference only touches 15 MPI symbols); when that
+build exists at baseline/_ref/bin/wordembedding this arm runs it.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "baseline", "_ref", "bin", "wordembedding")
+
+
+def unavailable(why: str) -> dict:
+    return {"impl": "reference", "unavailable": why}
+
+
+def run(args) -> dict:
+    if not os.path.exists(REF_BIN):
+        return unavailable("reference needs MPI/ZeroMQ (CMakeLists.txt:11 find_package(MPI REQUIRED)); "
+                           "neither exists in this image and pip cannot install a CMake C++ project "
+                           "without setup.py; no baseline/_ref/bin/wordembedding was built")
+    try:
+        from baseline import reference_runner
+        return reference_runner.run_wordembedding(REF_BIN, args)
+    except Exception as e:  # never crash the driver
+        return unavailable(f"reference run failed: {e!r}"[:300])

@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""Headline benchmark: WordEmbedding words/sec (BASELINE.json config 3) + MatrixTable Get/Add GB/s.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                   (the unmodified reference, if installable)
+
+Config (BASELINE.json): skip-gram, dim=300, vocab=1M, 5 negatives, window 5, synthetic Zipf
+corpus, fp32 tables and fp32 math (the reference's dtype), random-init weights.  One step =
+one data block of ``--block-words`` corpus words per GPU (weak scaling), trained through the
+public WordEmbedding API: RequestParameter -> K7 train kernel -> AddDeltaParameter.
+``value`` is device-timed (CUDA events, max over ranks); ``e2e`` adds, per step, the pinned
+host->device copy of the block's tokens and a device->host read of the loss.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "wordembedding_words_per_sec"
+CONFIG_MODEL = "WordEmbedding skip-gram dim=300 vocab=1M neg=5 window=5 (synthetic Zipf corpus)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--block-words", type=int, default=1 << 20)
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=300)
+    ap.add_argument("--negative", type=int, default=5)
+    ap.add_argument("--window", type=int, default=5)
+    ap.add_argument("--no-table-bw", action="store_true", help="skip the MatrixTable Get/Add sweep")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args) -> None:
+    """The reference arm: the UNMODIFIED reference from baseline/_ref through its own CLI."""
+    from baseline import reference_arm
+    print(json.dumps(reference_arm.run(args)), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import numpy as np
+    import torch
+    import multiverso_b200 as mv
+    from multiverso_b200.models.wordembedding import (WordEmbedding, WordEmbeddingOption,
+                                                      synthetic_zipf_corpus)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    mv.init()
+    rank = mv.rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    K, W, B = args.steps, max(args.warmup, 3), args.block_words
+
+    opt = WordEmbeddingOption(embeding_size=args.dim, window_size=args.window,
+                              negative_num=args.negative, init_learning_rate=0.025, sample=0.0,
+                              total_words=B * (K + W) * 2 * world, epoch=1)
+    we = WordEmbedding(opt, args.vocab, seed=1)
+
+    # synthetic corpus: a distinct block per step and per rank, staged in pinned host memory
+    n_blocks = K + W
+    corpus = synthetic_zipf_corpus(B * n_blocks, args.vocab, sentence_len=1000, seed=17 + rank)
+    pinned = torch.from_numpy(corpus).view(n_blocks, B).pin_memory()
+    dev_blocks = pinned.to(dev)               # device-timed arm: tokens already resident
+    words_per_block = int((corpus[:B] >= 0).sum())
+    tok_dev = torch.empty(B, dtype=torch.int32, device=dev)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        mv.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        we.learning_rate = opt.init_learning_rate * max(1e-4, 1.0 - i / (2.0 * n_blocks))
+        we.train_block(dev_blocks[i], compute_loss=True)
+
+    # ------------------------------------------------------------ device-timed arm
+    for i in range(W):
+        step_device(i)
+    sync_all()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    launches0 = we.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        step_device(W + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_local = ev0.elapsed_time(ev1)
+    launches = we.kernel_launches - launches0
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    pairs = int(we.pairs.item())
+    loss_per_pair = float(we.loss.item()) / max(pairs, 1)
+
+    # ------------------------------------------------------------ end-to-end arm
+    we2_steps = K
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(we2_steps):
+        tok_dev.copy_(pinned[W + i], non_blocking=True)          # H2D of this step's inputs
+        we.loss.zero_()
+        we.train_block(tok_dev, compute_loss=True)
+        loss_host.copy_(we.loss, non_blocking=False)             # D2H of the step's result
+    torch.cuda.synchronize()
+    e2e_s_local = time.perf_counter() - t0
+    sync_all()
+
+    # ------------------------------------------------------------ reduce over ranks (max time)
+    t = torch.tensor([ms_local, e2e_s_local * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = float(t[0]), float(t[1])
+    total_words = words_per_block * K * world
+    value = total_words / (ms_total / 1e3)
+    e2e_value = total_words / (e2e_ms_total / 1e3)
+
+    extra = {}
+    if not args.no_table_bw:
+        extra = table_bandwidth(mv, torch, world)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "words/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": "ours",
+            "config": {"model": CONFIG_MODEL, "global_batch": B * world, "seq_len": 1000,
+                       "parallelism": f"dp{world} row-sharded PS tables" if world > 1 else "1 GPU (worker+server)",
+                       "block_words_per_gpu": B, "l2": "tables 2.4 GB >> 126 MB L2; new token block every step",
+                       "pairs_per_word": pairs / max(1, words_per_block * (K + W)),
+                       "loss_per_pair": loss_per_pair},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "words/s", "h2d_bytes_per_step": B * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / K},
+            "gpu_launches": launches,
+            "extra": extra,
+        }
+        print(json.dumps(out), flush=True)
+    mv.shutdown()
+
+
+def table_bandwidth(mv, torch, world):
+    """BASELINE config 2: MatrixTable 1M x 512 fp32 whole-table Get and Add (fused updater),
+    device-timed, table bytes / time, max over ranks."""
+    rows, cols = 1_000_000, 512
+    out = {}
+    try:
+        t = mv.MatrixTable(rows, cols, "float32", updater="sgd")
+        nbytes = rows * cols * 4
+        delta = t.staging() if world > 1 else torch.full((rows * cols,), 1e-3, device="cuda")
+        if world > 1:
+            delta.fill_(1e-3)
+        buf = torch.empty(rows * cols, device="cuda")
+        res = {}
+        for name in ("add", "get"):
+            for it in range(2):
+                (t.add(delta, staged=world > 1) if name == "add" else t.get(buf))
+                if world > 1 and name == "add":
+                    delta = t.staging()
+            torch.cuda.synchronize()
+            mv.barrier()
+            n = 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for it in range(n):
+                if name == "add":
+                    t.wait(t.add_async(delta, staged=world > 1))
+                    if world > 1:
+                        delta = t.staging()
+                else:
+                    t.get(buf)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device="cuda")
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            res[name] = float(ms)
+            mv.barrier()
+        out = {"matrix_table": f"{rows}x{cols} fp32", "add_ms": res["add"], "get_ms": res["get"],
+               "add_gbs": nbytes / res["add"] / 1e6, "get_gbs": nbytes / res["get"] / 1e6,
+               "get_plus_add_gbs": 2 * nbytes / (res["add"] + res["get"]) / 1e6}
+    except Exception as e:  # the headline metric must still print
+        out = {"error": repr(e)[:200]}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,296 @@
+// multiverso-b200 :: C ABI of the sm_100a data-plane library (libmvb200.so).
+//
+// Every entry point takes raw device pointers + a cudaStream_t (as void*) so the
+// Python layer can drive it with torch tensors (tensor.data_ptr(), current stream)
+// through ctypes, and a C++ host program can link it directly. All functions
+// return 0 on success or a cudaError_t / negative library error; the message is
+// available from mvb_last_error().
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVB_MAX_RANKS 8
+#define MVB_PAD_CHANNELS 64            /* signal-pad channels per rank           */
+#define MVB_PAD_WORDS (MVB_PAD_CHANNELS * MVB_MAX_RANKS)
+#define MVB_EPOCH_FIN (1ull << 62)      /* ready-slot value of a worker that finished training */
+
+/* element types */
+enum { MVB_F32 = 0, MVB_F64 = 1, MVB_I32 = 2, MVB_I64 = 3, MVB_I8 = 4 };
+/* updaters (reference: -updater_type default|sgd|momentum_sgd|adagrad|dcasgd|dcasgda) */
+enum {
+  MVB_UPD_DEFAULT = 0,
+  MVB_UPD_SGD = 1,
+  MVB_UPD_MOMENTUM = 2,
+  MVB_UPD_ADAGRAD = 3,
+  MVB_UPD_DCASGD = 4,
+  MVB_UPD_DCASGDA = 5
+};
+
+/* Same 20-byte layout as the reference AddOption (updater.h:13-69):
+ * {worker_id, momentum, learning_rate, rho, lambda}. */
+typedef struct MvbAddOpt {
+  int worker_id;
+  float momentum;
+  float lr;
+  float rho;
+  float lambda;
+} MvbAddOpt;
+
+const char* mvb_last_error(void);
+int mvb_device_count(void);
+int mvb_set_device(int dev);
+int mvb_device_info(int dev, int* sms, int* cc_major, int* cc_minor, int64_t* total_mem);
+
+/* ---- symmetric memory (cudaMalloc + cudaIpc) ------------------------------ */
+int mvb_symm_alloc(int64_t bytes, void** out_ptr);
+int mvb_symm_free(void* ptr);
+int mvb_ipc_get_handle(void* ptr, void* handle64 /* 64 bytes */);
+int mvb_ipc_open_handle(const void* handle64, void** out_ptr);
+int mvb_ipc_close_handle(void* ptr);
+int mvb_enable_peer_access(int peer_dev);
+int mvb_can_access_peer(int dev, int peer, int* out);
+int mvb_memset_async(void* ptr, int value, int64_t bytes, void* stream);
+int mvb_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+int mvb_stream_sync(void* stream);
+int mvb_host_alloc_pinned(int64_t bytes, void** out);
+int mvb_host_free_pinned(void* p);
+
+/* ---- signal pads / device barrier (K11) ------------------------------------
+ * pads[r] = rank r's pad (uint64[MVB_PAD_WORDS]); slot(channel, src) on rank r is
+ * written by rank `src`. Epochs are monotonically increasing per channel. */
+int mvb_signal(void* const* pads, int me, int world, int channel, uint64_t epoch, void* stream);
+int mvb_wait(void* const* pads, int me, int world, int channel, uint64_t epoch,
+             uint32_t src_mask, int* err_flag, double timeout_s, void* stream);
+int mvb_barrier(void* const* pads, int me, int world, int channel, uint64_t epoch,
+                int* err_flag, double timeout_s, void* stream);
+
+/* ---- dense Add / Get (K1, K2) ----------------------------------------------
+ * mvb_add_dense_fused: owner-side reduce-scatter + updater. The owner pulls its
+ * slice [shard_off, shard_off+shard_len) from each of `nworkers` staging buffers
+ * (delta_ptrs[w], full-table sized, peer-mapped) and applies the updater once per
+ * worker in worker order, in registers, writing the shard (and state) once.
+ * If pads != NULL the kernel first publishes (channel ch_ready) that this rank's
+ * staging buffer is complete and waits for all workers in worker_mask, and on
+ * completion publishes ch_done (consumed by mvb_get_dense).  */
+typedef struct MvbDenseAdd {
+  int dtype;              /* MVB_F32 | MVB_F64 | MVB_I32 */
+  int updater;            /* MVB_UPD_*                   */
+  void* shard;            /* local shard                 */
+  void* state0;           /* updater state slab(s)       */
+  void* state1;
+  int64_t shard_len;      /* elements                    */
+  int64_t shard_off;      /* element offset in staging   */
+  int64_t state_stride;   /* elements between per-worker state slabs */
+  int nworkers;
+  uint32_t worker_mask;   /* which workers contribute    */
+  const void* delta_ptrs[MVB_MAX_RANKS]; /* indexed by worker id */
+  MvbAddOpt opts[MVB_MAX_RANKS];         /* per worker          */
+  float scale;            /* delta pre-scale (1 = none)  */
+  float clip;             /* |delta| clip, 0 = off       */
+  /* fused signalling (optional) */
+  void* const* pads;      /* host array[world] of pad pointers or NULL */
+  int me, world;
+  int ch_ready, ch_done;
+  uint64_t epoch;
+  int worker_rank[MVB_MAX_RANKS]; /* worker id -> rank (for flag slots) */
+  int is_worker;          /* this rank publishes ch_ready             */
+  int* err_flag;          /* device int, set on watchdog timeout      */
+  int* fin_flag;          /* device int, set to 1 when every worker has finished */
+  unsigned int* done_counter; /* device uint, zero-initialised         */
+  double timeout_s;
+} MvbDenseAdd;
+int mvb_add_dense_fused(const MvbDenseAdd* a, void* stream);
+
+/* Local (single-source) updater apply: the stand-alone K9 kernel used by the
+ * NCCL comparator path and by row-wise / whole adds with one worker. */
+int mvb_updater_apply(int dtype, int updater, void* data, const void* delta, void* state0,
+                      void* state1, int64_t n, const MvbAddOpt* opt, float scale, void* stream);
+
+/* mvb_get_dense: all-gather by pull. shard_ptrs[s] = server s's shard (peer-mapped),
+ * shard_offs[s]/shard_lens[s] in elements, out = local full-size buffer. If pads
+ * != NULL waits for ch_done >= epoch from every server rank first. */
+typedef struct MvbDenseGet {
+  int dtype;
+  void* out;
+  int nservers;
+  const void* shard_ptrs[MVB_MAX_RANKS];
+  int64_t shard_offs[MVB_MAX_RANKS];
+  int64_t shard_lens[MVB_MAX_RANKS];
+  void* const* pads;
+  int me, world;
+  int ch_done;
+  uint64_t epoch;
+  int server_rank[MVB_MAX_RANKS];
+  int* err_flag;
+  double timeout_s;
+} MvbDenseGet;
+int mvb_get_dense(const MvbDenseGet* g, void* stream);
+
+/* One-sided async push: red.add of (sign * delta[shard range]) into every owner's
+ * shard through the peer mapping. Stateless updaters only (default: +, sgd: -). */
+int mvb_push_dense_red(int dtype, const void* delta, int nservers, void* const* shard_ptrs,
+                       const int64_t* shard_offs, const int64_t* shard_lens, float sign,
+                       void* stream);
+
+/* ---- row-sparse Get / Add (K3, K4, K10) ------------------------------------ */
+typedef struct MvbRowMap {
+  int64_t num_row, num_col;
+  int nservers;
+  int64_t rows_per_server;            /* reference rule: num_row / nservers      */
+  void* shard_ptrs[MVB_MAX_RANKS];    /* server s shard base (rows [s*rps, ...)) */
+} MvbRowMap;
+int mvb_get_rows(int dtype, const MvbRowMap* m, const int64_t* row_ids, int64_t k, void* out,
+                 int64_t out_ld, void* stream);
+int mvb_add_rows_red(int dtype, const MvbRowMap* m, const int64_t* row_ids, int64_t k,
+                     const void* vals, int64_t vals_ld, float sign, void* stream);
+/* Stateful row add applied by the OWNER on its local shard for rows in its range:
+ * ids/vals may be another rank's (peer-mapped) staging. */
+int mvb_add_rows_owner(int dtype, int updater, void* shard, void* state0, void* state1,
+                       int64_t row_lo, int64_t row_hi, int64_t num_col, int64_t state_stride,
+                       const int64_t* row_ids, int64_t k, const void* vals, int64_t vals_ld,
+                       const MvbAddOpt* opt, void* stream);
+int mvb_row_nonzero_mask(int dtype, const void* data, int64_t rows, int64_t cols, int64_t ld,
+                         uint8_t* mask, void* stream);
+/* stale-row bitmap (T4/T5 delta-pull): mark rows stale for all workers / query+clear */
+int mvb_stale_mark(uint8_t* stale /*[workers][rows]*/, int64_t rows, int nworkers,
+                   const int64_t* row_ids, int64_t k /* k<0: all rows */, void* stream);
+int mvb_stale_take(uint8_t* stale_w /*[rows] for one worker*/, int64_t rows,
+                   const int64_t* row_ids, int64_t k, uint8_t* out_mask, void* stream);
+
+/* ---- KV hash table (K5) ----------------------------------------------------- */
+/* open addressing, keys int64 (empty = INT64_MIN), values 8 bytes (f64 or i64) or 4
+ * bytes (f32 / i32). Owner of key = mod(key, nservers). */
+typedef struct MvbKV {
+  int vtype;                       /* MVB_F32|MVB_F64|MVB_I32|MVB_I64 */
+  int nservers;
+  int64_t capacity;                /* slots per shard (power of two)  */
+  void* keys[MVB_MAX_RANKS];       /* int64[capacity] per server      */
+  void* vals[MVB_MAX_RANKS];
+} MvbKV;
+int mvb_kv_init(void* keys, int64_t capacity, void* stream);
+int mvb_kv_add(const MvbKV* kv, const int64_t* keys, const void* vals, int64_t n, int* err_flag,
+               void* stream);
+int mvb_kv_get(const MvbKV* kv, const int64_t* keys, void* out_vals, int64_t n, void* stream);
+int mvb_kv_dump(int vtype, const void* keys, const void* vals, int64_t capacity,
+                int64_t* out_keys, void* out_vals, int64_t* out_count, void* stream);
+
+/* ---- all-reduce (K6) --------------------------------------------------------- */
+/* One-shot P2P: every rank reads all peers' symmetric buffers and reduces locally
+ * in fixed rank order (deterministic, identical on all ranks). Two-shot: reduce own
+ * slice, then write it to every peer. In-kernel signalling on channels ch..ch+1. */
+typedef struct MvbAllreduce {
+  int dtype;
+  int64_t n;
+  void* bufs[MVB_MAX_RANKS];    /* symmetric staging, peer-mapped */
+  void* out;                    /* local result (may alias bufs[me] for two-shot) */
+  void* const* pads;
+  int me, world;
+  int ch;
+  uint64_t epoch;
+  int* err_flag;
+  unsigned int* done_counter;
+  double timeout_s;
+} MvbAllreduce;
+int mvb_allreduce_oneshot(const MvbAllreduce* a, void* stream);
+int mvb_allreduce_twoshot(const MvbAllreduce* a, void* stream);
+
+/* ---- WordEmbedding (K7) -------------------------------------------------------- */
+typedef struct MvbSgns {
+  const int* tokens;         /* word ids, <0 = sentence break            */
+  int64_t n_tokens;
+  float* w_in;               /* input embeddings  [rows x ld]             */
+  float* w_out;              /* output embeddings [rows x ld]             */
+  float* g2_in;              /* AdaGrad G^2 (or NULL)                     */
+  float* g2_out;
+  int dim;
+  int64_t ld;
+  int window;
+  int negative;              /* K (0 when hs)                             */
+  int cbow;                  /* 0 skip-gram, 1 cbow                       */
+  int hs;                    /* hierarchical softmax                      */
+  int use_adagrad;
+  float lr;
+  /* negative sampling: alias table over vocab (prob,alias), or an explicit pool */
+  const float* alias_prob;
+  const int* alias_idx;
+  int vocab;
+  const int* neg_pool;
+  int neg_pool_size;
+  /* hierarchical softmax: per word path [codelen<=MVB_MAX_CODE] */
+  const int* hs_points;      /* [vocab x max_code] inner-node row ids      */
+  const int8_t* hs_codes;    /* [vocab x max_code]                         */
+  const int* hs_len;         /* [vocab]                                    */
+  int hs_max_code;
+  /* optional global-id -> local-slot maps (block mode); NULL = identity   */
+  const int* map_in;
+  const int* map_out;
+  uint64_t seed;
+  float* loss_sum;           /* optional: += sum of -log sigma(..)         */
+  unsigned long long* pair_count;  /* optional: += trained (input,target) samples */
+} MvbSgns;
+int mvb_sgns_train(const MvbSgns* a, void* stream);
+int mvb_build_alias_table(const double* weights_host, int n, float* prob_host, int* alias_host);
+
+/* ---- LogisticRegression (K8) ---------------------------------------------------- */
+/* sparse CSR minibatch: objective 0 linear(squared) 1 sigmoid 2 softmax(dense only) */
+typedef struct MvbLrSparse {
+  const int64_t* row_ptr;    /* [n+1]                      */
+  const int64_t* keys;       /* [nnz] feature ids          */
+  const float* vals;         /* [nnz] (NULL => 1.0)        */
+  const float* labels;       /* [n]                        */
+  const float* sample_w;     /* [n] or NULL                */
+  int64_t n;
+  int objective;
+  const float* w;            /* dense weight vector (pulled table) [dim*out] */
+  int64_t dim;               /* input_size incl. bias      */
+  int out;                   /* output classes (1 for binary) */
+  float* grad;               /* [dim*out] accumulated += g*x / n  (atomic)  */
+  float* loss_sum;           /* scalar                      */
+  int* correct;              /* scalar: # correct predictions */
+  float* pred;               /* optional [n*out]            */
+  float* err;                /* scratch [n*out]: (p - y) * weight / n */
+  int compute_grad;          /* 0 = predict only            */
+} MvbLrSparse;
+int mvb_lr_sparse_fwd_bwd(const MvbLrSparse* a, void* stream);
+typedef struct MvbLrDense {
+  const float* x;            /* [n x dim] row-major (bias column included) */
+  const float* labels;       /* [n] class index or target                   */
+  int64_t n, dim;
+  int out;
+  int objective;
+  const float* w;            /* [out x dim]                                 */
+  float* grad;               /* [out x dim]  = (1/n) sum (p-y) x^T          */
+  float* loss_sum;
+  int* correct;
+  float* pred;               /* optional [n x out]                          */
+  float* err;                /* scratch [n x out]                           */
+  int compute_grad;
+} MvbLrDense;
+int mvb_lr_dense_fwd_bwd(const MvbLrDense* a, void* stream);
+/* FTRL-proximal: weights from (z,n); gradient emits (dz,dn) (reference objective.cpp:260-336) */
+int mvb_ftrl_weights(const float* z, const float* n, float* w, int64_t len, float alpha, float beta,
+                     float l1, float l2, void* stream);
+int mvb_ftrl_update(float* z, float* n, const float* w, const float* g, int64_t len, float alpha,
+                    void* stream);
+/* regulariser add: 1 = L1 sign(w)*c, 2 = L2 w*c */
+int mvb_regularize(float* grad, const float* w, int64_t len, int type, float coef, void* stream);
+
+/* ---- fused Get + GEMM (tcgen05 / TMEM / TMA) -------------------------------------- */
+/* Y[M x N] = X[M x K] * W[N x K]^T where W's rows are sharded over servers (row-range
+ * partition, peer-mapped); optionally also materialises W into w_cache (the Get). */
+typedef struct MvbGetGemm {
+  const float* x;            /* [M x K] fp32 row-major, local     */
+  float* y;                  /* [M x N] fp32                      */
+  float* w_cache;            /* optional [N x K] local copy       */
+  int64_t M, N, K;
+  MvbRowMap wmap;            /* N rows x K cols over servers      */
+} MvbGetGemm;
+int mvb_get_gemm_fused(const MvbGetGemm* g, void* stream);
+int mvb_get_gemm_supported(void);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,159 @@
+"""In-tree native build of multiverso-b200.
+
+Two artefacts, both built with explicit compiler invocations (no JIT cache, so the
+``.so`` files travel with the repo snapshot to the GPU box):
+
+* ``multiverso_b200/_lib/libmvb200.so``      -- sm_100a data-plane kernels (nvcc,
+  ``-gencode arch=compute_100a,code=sm_100a -lineinfo``), sources ``csrc/cuda/*.cu``
+* ``multiverso_b200/_lib/libmultiverso.so``  -- C++17 host runtime + C API (g++),
+  sources ``csrc/host/**/*.cpp``; plus the native tools/apps under ``build/bin``.
+
+Objects are cached under ``build/`` and rebuilt only when a source or header is newer.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+LIBDIR = Path(__file__).resolve().parent / "_lib"
+BUILD = ROOT / "build"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-pthread", "-fopenmp"]
+
+
+def _newer(src_list, target: Path) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(s).stat().st_mtime > t for s in src_list)
+
+
+def _run(cmd, what):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{what} failed:\n{' '.join(map(str, cmd))}\n{r.stdout}\n{r.stderr}")
+    return r
+
+
+def _find(tool, fallback):
+    p = shutil.which(tool)
+    if p:
+        return p
+    return fallback if Path(fallback).exists() else None
+
+
+def build_cuda(verbose: bool = False) -> Path:
+    """Compile csrc/cuda/*.cu for sm_100a and link libmvb200.so."""
+    nvcc = _find("nvcc", "/usr/local/cuda/bin/nvcc")
+    out = LIBDIR / "libmvb200.so"
+    srcs = sorted((ROOT / "csrc" / "cuda").glob("*.cu"))
+    hdrs = sorted((ROOT / "csrc" / "cuda").glob("*.h")) + sorted((ROOT / "csrc" / "cuda").glob("*.cuh"))
+    if nvcc is None:
+        if out.exists():
+            return out
+        raise RuntimeError("nvcc not found and libmvb200.so not prebuilt")
+    objdir = BUILD / "cuda"
+    objdir.mkdir(parents=True, exist_ok=True)
+    LIBDIR.mkdir(parents=True, exist_ok=True)
+    inc = []
+    cutlass = _cutlass_include()
+    if cutlass:
+        inc = ["-I", str(cutlass)]
+
+    def one(src: Path):
+        obj = objdir / (src.stem + ".o")
+        if _newer([src] + hdrs, obj):
+            if verbose:
+                print(f"[build] nvcc {src.name}", flush=True)
+            _run([nvcc, *NVCC_FLAGS, *inc, "-c", str(src), "-o", str(obj)], f"nvcc {src.name}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs) or 1)) as ex:
+        objs = list(ex.map(one, srcs))
+    if _newer(objs, out):
+        _run([nvcc, "-shared", "-o", str(out), *map(str, objs), "-lcuda"], "link libmvb200.so")
+    return out
+
+
+def _cutlass_include():
+    try:
+        import flashinfer  # noqa: F401
+        p = Path(flashinfer.__file__).parent / "data" / "cutlass" / "include"
+        if p.exists():
+            return p
+    except Exception:
+        pass
+    return None
+
+
+def build_host(verbose: bool = False) -> Path:
+    """Compile the C++17 host runtime (csrc/host) into libmultiverso.so and build the
+    native test / app executables under build/bin."""
+    cxx = _find("g++", "/usr/bin/g++")
+    out = LIBDIR / "libmultiverso.so"
+    srcdir = ROOT / "csrc" / "host"
+    srcs = sorted(p for p in srcdir.rglob("*.cpp") if "apps" not in p.parts and "tools" not in p.parts)
+    if not srcs:
+        return out
+    hdrs = sorted((ROOT / "include").rglob("*.h")) + sorted(srcdir.rglob("*.h"))
+    if cxx is None:
+        if out.exists():
+            return out
+        raise RuntimeError("g++ not found and libmultiverso.so not prebuilt")
+    objdir = BUILD / "host"
+    objdir.mkdir(parents=True, exist_ok=True)
+    LIBDIR.mkdir(parents=True, exist_ok=True)
+    inc = ["-I", str(ROOT / "include"), "-I", str(srcdir)]
+
+    def one(src: Path):
+        rel = src.relative_to(srcdir)
+        obj = objdir / ("_".join(rel.with_suffix("").parts) + ".o")
+        if _newer([src] + hdrs, obj):
+            if verbose:
+                print(f"[build] g++ {rel}", flush=True)
+            _run([cxx, *CXX_FLAGS, *inc, "-c", str(src), "-o", str(obj)], f"g++ {rel}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, srcs))
+    if _newer(objs, out):
+        _run([cxx, "-shared", "-o", str(out), *map(str, objs), "-pthread", "-fopenmp", "-ldl"],
+             "link libmultiverso.so")
+    # executables: each csrc/host/{apps,tools}/<name>/*.cpp -> build/bin/<name>
+    bindir = BUILD / "bin"
+    bindir.mkdir(parents=True, exist_ok=True)
+    for group in ("apps", "tools"):
+        gdir = srcdir / group
+        if not gdir.exists():
+            continue
+        for appdir in sorted(p for p in gdir.iterdir() if p.is_dir()):
+            asrcs = sorted(appdir.glob("*.cpp"))
+            if not asrcs:
+                continue
+            exe = bindir / appdir.name
+            if _newer(asrcs + hdrs + [out], exe):
+                if verbose:
+                    print(f"[build] link {exe.name}", flush=True)
+                _run([cxx, *CXX_FLAGS, *inc, "-I", str(appdir), *map(str, asrcs), "-o", str(exe),
+                      f"-L{LIBDIR}", "-lmultiverso", f"-Wl,-rpath,{LIBDIR}", "-pthread", "-fopenmp"],
+                     f"link {exe.name}")
+    return out
+
+
+def build_all(verbose: bool = False):
+    build_host(verbose)
+    build_cuda(verbose)
+
+
+if __name__ == "__main__":
+    build_all(verbose=True)
+    print("ok")

@@ -1,0 +1,110 @@
+"""Public API: the reference's MV_* surface (include/multiverso/multiverso.h:9-65) and the
+Python binding's names (binding/python/multiverso/api.py:12-75).
+
+The same calls work on both backends: ``device`` (CUDA present: HBM tables + sm_100a
+kernels) and ``host`` (no CUDA: the C++ runtime in libmultiverso.so, TCP control plane).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+from .runtime import Runtime
+from .utils import FLAGS, Dashboard, Log
+
+
+def _rt() -> Runtime:
+    return Runtime.get()
+
+
+def init(argv: Optional[List[str]] = None, sync: Optional[bool] = None, **flags) -> List[str]:
+    """MV_Init. ``sync=True`` selects the BSP server like ``mv.init(sync=True)`` in the
+    reference binding (api.py:12-35). Extra keyword flags are MV_SetFlag'ed first.
+    Returns argv with the recognised ``-key=value`` flags removed."""
+    if sync is not None:
+        flags["sync"] = bool(sync)
+    rt = _rt()
+    rest = rt.start(argv, **flags)
+    if rt.backend == "host":
+        from . import host
+        host.init_backend(rt)
+    return rest
+
+
+def shutdown(finalize_net: bool = True) -> None:
+    """MV_ShutDown(finalize_net): ``False`` keeps the process group alive so the process
+    can MV_Init again (Test/unittests/multiverso_env.h:15-17)."""
+    rt = _rt()
+    if rt.backend == "host" and rt.started:
+        from . import host
+        host.shutdown_backend(rt, finalize_net)
+    from .parallel import collectives
+    collectives.reset()
+    rt.stop(finalize_net)
+
+
+def barrier() -> None:
+    """MV_Barrier."""
+    rt = _rt()
+    if rt.backend == "host" and rt.started:
+        from . import host
+        host.barrier()
+    else:
+        rt.barrier()
+
+
+def rank() -> int: return _rt().rank
+def size() -> int: return _rt().size
+def num_workers() -> int: return _rt().num_workers()
+def num_servers() -> int: return _rt().num_servers()
+def workers_num() -> int: return _rt().num_workers()   # python binding name
+def worker_id() -> int: return _rt().worker_id()
+def server_id() -> int: return _rt().server_id()
+def worker_id_to_rank(wid: int) -> int: return _rt().worker_id_to_rank(wid)
+def server_id_to_rank(sid: int) -> int: return _rt().server_id_to_rank(sid)
+def is_master_worker() -> bool: return _rt().worker_id() == 0
+
+
+def set_flag(name: str, value) -> None:
+    """MV_SetFlag<T>(name, value)."""
+    FLAGS.set(name, value)
+
+
+def aggregate(data):
+    """MV_Aggregate: in-place SUM all-reduce (model-averaging mode)."""
+    rt = _rt()
+    import torch
+    if rt.backend == "device":
+        from .parallel import aggregate as _agg
+        t = data if torch.is_tensor(data) and data.is_cuda else torch.as_tensor(data).to(rt.device)
+        _agg(t)
+        if t is not data:
+            if torch.is_tensor(data):
+                data.copy_(t.cpu())
+            else:
+                import numpy as np
+                np.copyto(data, t.cpu().numpy())
+        return data
+    from . import host
+    return host.aggregate(data)
+
+
+def net_bind(rank_: int, endpoint: str) -> None:
+    """MV_NetBind (explicit-endpoint bootstrap of the control plane, C# path)."""
+    from . import host
+    host.net_bind(rank_, endpoint)
+
+
+def net_connect(ranks: List[int], endpoints: List[str]) -> None:
+    """MV_NetConnect."""
+    from . import host
+    host.net_connect(ranks, endpoints)
+
+
+def net_finalize() -> None:
+    """MV_NetFinalize."""
+    from . import host
+    host.net_finalize()
+
+
+def dashboard_display() -> None:
+    Dashboard.display()

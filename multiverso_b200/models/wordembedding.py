@@ -1,0 +1,299 @@
+"""WordEmbedding (word2vec: skip-gram / CBOW x negative sampling / hierarchical softmax).
+
+Reference application: Applications/WordEmbedding.  The training maths is
+WordEmbedding::TrainSample / FeedForward / BPOutputLayer (src/wordembedding.cpp:57-166), the
+parameter-server glue is Communicator (src/communicator.cpp): two MatrixTables
+(input rows U(-0.5/dim, 0.5/dim), output rows zero), optional AdaGrad G^2 tables, a KVTable
+for the global word count, per data block RequestParameter -> train -> AddDeltaParameter
+with delta = (trained - server_now) / num_workers.
+
+B200 mapping
+------------
+* ``world == 1``: the shard *is* the table, so the block protocol degenerates exactly
+  ((trained - cur)/1 added back == trained) and the K7 kernel trains in place on the HBM
+  resident shards -- no gather, no scatter.
+* ``world > 1`` (block mode = reference semantics): device-side PrepareData (unique input
+  rows + negative pool), K4 row gather of the needed rows over NVLink into a local block
+  cache, K7 on the cache through id->slot maps, K3 scatter-add of (new - old)/W.
+* learning-rate decay follows UpdateLearningRate (wordembedding.cpp:38-47) from the global
+  word count kept in the KV table (constant.h: kWordCountId).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..runtime import Runtime
+from ..tables.device import KVDeviceTable, MatrixDeviceTable
+from ..utils import Log, monitor
+
+K_WORD_COUNT_ID = 4  # constant.h:16-20
+
+
+@dataclass
+class WordEmbeddingOption:
+    """The 21 CLI flags of the reference (util.cpp:31-56) with its defaults (util.cpp:6-29)."""
+    train_file: Optional[str] = None
+    read_vocab_file: Optional[str] = None
+    output_file: Optional[str] = None
+    sw_file: Optional[str] = None
+    endpoints_file: Optional[str] = None
+    hs: bool = False
+    output_binary: bool = False
+    cbow: bool = False
+    stopwords: bool = False
+    use_adagrad: bool = False
+    is_pipeline: bool = False
+    sample: float = 0.0
+    data_block_size: int = 1 << 20
+    embeding_size: int = 100
+    thread_cnt: int = 1
+    window_size: int = 5
+    negative_num: int = 5
+    min_count: int = 5
+    epoch: int = 1
+    total_words: int = 0
+    max_preload_data_size: int = 8 << 30
+    init_learning_rate: float = 0.025
+
+
+class HuffmanTables:
+    """Device copy of the Huffman paths (HuffmanEncoder::BuildHuffmanTreeFromDict,
+    huffman_encoder.cpp:87-196): per word the inner-node ids and branch codes."""
+
+    def __init__(self, counts: np.ndarray, device):
+        import heapq
+        V = len(counts)
+        heap = [(int(c), i) for i, c in enumerate(counts)]
+        heapq.heapify(heap)
+        parent = np.zeros(2 * V, dtype=np.int64)
+        binary = np.zeros(2 * V, dtype=np.int8)
+        nxt = V
+        while len(heap) > 1:
+            c1, a = heapq.heappop(heap)
+            c2, b = heapq.heappop(heap)
+            parent[a] = nxt
+            parent[b] = nxt
+            binary[b] = 1
+            heapq.heappush(heap, (c1 + c2, nxt))
+            nxt += 1
+        root = nxt - 1
+        codes, points, lens = [], [], np.zeros(V, dtype=np.int32)
+        maxlen = 1
+        for w in range(V):
+            code, point, n = [], [], w
+            while n != root and V > 1:
+                code.append(int(binary[n]))
+                n = int(parent[n])
+                point.append(n - V)
+            code.reverse()
+            point.reverse()
+            codes.append(code)
+            points.append(point)
+            lens[w] = len(code)
+            maxlen = max(maxlen, len(code))
+        self.max_code = maxlen
+        P = np.zeros((V, maxlen), dtype=np.int32)
+        Cd = np.zeros((V, maxlen), dtype=np.int8)
+        for w in range(V):
+            P[w, :lens[w]] = points[w]
+            Cd[w, :lens[w]] = codes[w]
+        self.points = torch.from_numpy(P).to(device)
+        self.codes = torch.from_numpy(Cd).to(device)
+        self.lens = torch.from_numpy(lens).to(device)
+
+
+class WordEmbedding:
+    """Distributed word2vec trainer on HBM-resident tables."""
+
+    def __init__(self, option: WordEmbeddingOption, vocab_size: int,
+                 word_counts: Optional[np.ndarray] = None, seed: int = 1):
+        rt = Runtime.get()
+        if rt.backend != "device":
+            Log.fatal("WordEmbedding needs the device backend (CUDA)")
+        self.rt, self.opt, self.V = rt, option, int(vocab_size)
+        self.D = int(option.embeding_size)
+        self.dev = rt.device
+        self.W = max(rt.num_workers(), 1)
+        D = self.D
+        # PrepareParameterTables (communicator.cpp:17-32)
+        self.input_table = MatrixDeviceTable(self.V, D, "float32", updater="default",
+                                             min_value=-0.5 / D, max_value=0.5 / D, seed=seed)
+        self.output_table = MatrixDeviceTable(self.V, D, "float32", updater="default", init_value=0.0)
+        self.g2_in = self.g2_out = None
+        if option.use_adagrad:
+            self.g2_in = MatrixDeviceTable(self.V, D, "float32", updater="default", init_value=0.0)
+            self.g2_out = MatrixDeviceTable(self.V, D, "float32", updater="default", init_value=0.0)
+        self.wordcount_table = KVDeviceTable("int64", "int64", capacity=1024)
+        if word_counts is None:
+            word_counts = 1.0 / np.arange(1, self.V + 1, dtype=np.float64)   # Zipf
+        self.counts = np.asarray(word_counts, dtype=np.float64)
+        # Sampler::SetNegativeSamplingDistribution (util.cpp:116-135): unigram^0.75
+        if option.negative_num > 0 and not option.hs:
+            prob = np.empty(self.V, dtype=np.float32)
+            alias = np.empty(self.V, dtype=np.int32)
+            w = np.power(self.counts, 0.75)
+            rc = N.cuda_lib().mvb_build_alias_table(
+                w.ctypes.data_as(C.c_void_p), C.c_int(self.V), prob.ctypes.data_as(C.c_void_p),
+                alias.ctypes.data_as(C.c_void_p))
+            if rc != 0:
+                Log.fatal("alias table construction failed (%d)", rc)
+            self.alias_prob = torch.from_numpy(prob).to(self.dev)
+            self.alias_idx = torch.from_numpy(alias).to(self.dev)
+        else:
+            self.alias_prob = self.alias_idx = None
+        self.huffman = HuffmanTables(self.counts * 1e9, self.dev) if option.hs else None
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.pairs = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.word_count_actual = 0
+        self.learning_rate = float(option.init_learning_rate)
+        self._step = 0
+        self._map_in = self._map_out = None
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ lr schedule
+    def update_learning_rate(self) -> float:
+        o = self.opt
+        if not o.use_adagrad and o.total_words > 0:
+            lr = o.init_learning_rate * (1 - self.word_count_actual / (o.total_words * o.epoch + 1.0))
+            self.learning_rate = max(lr, o.init_learning_rate * 1e-4)
+        return self.learning_rate
+
+    # ------------------------------------------------------------------ K7 launch
+    def _launch(self, tokens: torch.Tensor, w_in, w_out, g2_in, g2_out, ld, map_in=None,
+                map_out=None, neg_pool=None, compute_loss=True) -> None:
+        o = self.opt
+        a = N.Sgns()
+        a.tokens, a.n_tokens = tokens.data_ptr(), tokens.numel()
+        a.w_in, a.w_out = w_in.data_ptr(), w_out.data_ptr()
+        a.g2_in = g2_in.data_ptr() if g2_in is not None else None
+        a.g2_out = g2_out.data_ptr() if g2_out is not None else None
+        a.dim, a.ld = self.D, ld
+        a.window, a.negative = o.window_size, (0 if o.hs else o.negative_num)
+        a.cbow, a.hs, a.use_adagrad = int(o.cbow), int(o.hs), int(o.use_adagrad)
+        a.lr = self.learning_rate if not o.use_adagrad else o.init_learning_rate
+        a.alias_prob = N.ptr(self.alias_prob)
+        a.alias_idx = N.ptr(self.alias_idx)
+        a.vocab = self.V
+        a.neg_pool = N.ptr(neg_pool)
+        a.neg_pool_size = neg_pool.numel() if neg_pool is not None else 0
+        if self.huffman is not None:
+            a.hs_points, a.hs_codes = self.huffman.points.data_ptr(), self.huffman.codes.data_ptr()
+            a.hs_len, a.hs_max_code = self.huffman.lens.data_ptr(), self.huffman.max_code
+        a.map_in, a.map_out = N.ptr(map_in), N.ptr(map_out)
+        self._step += 1
+        a.seed = ((0x5DEECE66D * (self.rt.rank + 1)) ^ (self._step * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+        a.loss_sum = self.loss.data_ptr() if compute_loss else None
+        a.pair_count = self.pairs.data_ptr()
+        N.check(N.cuda_lib().mvb_sgns_train(C.byref(a), C.c_void_p(N.stream_ptr())), "mvb_sgns_train")
+        self.kernel_launches += 1
+
+    # ------------------------------------------------------------------ one data block
+    def train_block(self, tokens: torch.Tensor, compute_loss: bool = True) -> None:
+        """Train on one block of token ids (int32 CUDA tensor, negative = sentence break).
+        Asynchronous on the current stream; read ``loss`` / ``pairs`` after a sync."""
+        assert tokens.is_cuda and tokens.dtype == torch.int32
+        if self.rt.size == 1:
+            with monitor("WE_TRAIN_BLOCK", cuda=True):
+                self._launch(tokens, self.input_table.shard, self.output_table.shard,
+                             None if self.g2_in is None else self.g2_in.shard,
+                             None if self.g2_out is None else self.g2_out.shard, self.D,
+                             compute_loss=compute_loss)
+            return
+        self._train_block_distributed(tokens, compute_loss)
+
+    def _train_block_distributed(self, tokens: torch.Tensor, compute_loss: bool) -> None:
+        o, dev, V, D = self.opt, self.dev, self.V, self.D
+        with monitor("WE_PREPARE_DATA", cuda=True):
+            valid = tokens[tokens >= 0].to(torch.int64)
+            in_ids = torch.unique(valid)
+            neg_pool = None
+            if o.hs:
+                # output nodes = inner nodes on the Huffman paths of the block's words
+                pts = self.huffman.points[in_ids]
+                ln = self.huffman.lens[in_ids].to(torch.int64)
+                m = torch.arange(pts.shape[1], device=dev)[None, :] < ln[:, None]
+                out_ids = torch.unique(pts[m].to(torch.int64))
+            else:
+                # PrepareData: negative_num * |input| draws form the block's negative pool
+                n_draw = o.negative_num * in_ids.numel()
+                idx = torch.randint(0, V, (n_draw,), device=dev)
+                u = torch.rand(n_draw, device=dev)
+                pool = torch.where(u < self.alias_prob[idx], idx, self.alias_idx[idx].to(torch.int64))
+                neg_pool = pool.to(torch.int32)
+                out_ids = torch.unique(torch.cat([in_ids, pool]))
+            if self._map_in is None:
+                self._map_in = torch.full((V,), -1, dtype=torch.int32, device=dev)
+                self._map_out = torch.full((V,), -1, dtype=torch.int32, device=dev)
+            self._map_in[in_ids] = torch.arange(in_ids.numel(), dtype=torch.int32, device=dev)
+            self._map_out[out_ids] = torch.arange(out_ids.numel(), dtype=torch.int32, device=dev)
+        # RequestParameter (communicator.cpp:117-155): pull the block's rows
+        cache_in = self.input_table.get_rows(in_ids)
+        cache_out = self.output_table.get_rows(out_ids)
+        old_in, old_out = cache_in.clone(), cache_out.clone()
+        g2i = g2o = None
+        if o.use_adagrad:
+            g2i = self.g2_in.get_rows(in_ids)
+            g2o = self.g2_out.get_rows(out_ids)
+            old_g2i, old_g2o = g2i.clone(), g2o.clone()
+        with monitor("WE_TRAIN_BLOCK", cuda=True):
+            self._launch(tokens, cache_in, cache_out, g2i, g2o, D, self._map_in, self._map_out,
+                         neg_pool, compute_loss)
+        # AddDeltaParameter (communicator.cpp:206-249): delta = (trained - pulled) / W
+        inv = 1.0 / self.W
+        self.input_table.add_rows(in_ids, (cache_in - old_in) * inv)
+        self.output_table.add_rows(out_ids, (cache_out - old_out) * inv)
+        if o.use_adagrad:
+            self.g2_in.add_rows(in_ids, (g2i - old_g2i) * inv)
+            self.g2_out.add_rows(out_ids, (g2o - old_g2o) * inv)
+
+    # ------------------------------------------------------------------ word count (KV)
+    def add_word_count(self, n: int) -> None:
+        self.wordcount_table.add(K_WORD_COUNT_ID, int(n))
+
+    def get_word_count(self) -> int:
+        self.word_count_actual = int(self.wordcount_table.get(K_WORD_COUNT_ID))
+        return self.word_count_actual
+
+    # ------------------------------------------------------------------ results
+    def embeddings(self) -> torch.Tensor:
+        """Whole input-embedding matrix [V, D] (SaveEmbedding pulls it in 100k-row batches)."""
+        return self.input_table.get().view(self.V, self.D)
+
+    def save_embedding(self, path: str, words=None, binary: bool = False) -> None:
+        """word2vec text / binary format (distributed_wordembedding.cpp:263-325); rank 0 only."""
+        if self.rt.rank != 0:
+            return
+        batch = 100000
+        with open(path, "wb") as f:
+            f.write(f"{self.V} {self.D}\n".encode())
+            for lo in range(0, self.V, batch):
+                hi = min(self.V, lo + batch)
+                rows = self.input_table.get_rows(torch.arange(lo, hi, device=self.dev)).cpu().numpy()
+                for i in range(hi - lo):
+                    w = words[lo + i] if words is not None else str(lo + i)
+                    if binary:
+                        f.write(w.encode() + b" " + rows[i].astype(np.float32).tobytes() + b"\n")
+                    else:
+                        f.write((w + " " + " ".join(f"{x:.6f}" for x in rows[i]) + "\n").encode())
+
+
+def synthetic_zipf_corpus(n_tokens: int, vocab: int, sentence_len: int = 1000, seed: int = 0,
+                          exponent: float = 1.0) -> np.ndarray:
+    """Synthetic corpus of the benchmark shape: Zipf(``exponent``) word ids over ``vocab``
+    words, sentences of ``sentence_len`` tokens (kMaxSentenceLength, constant.h:27) separated
+    by -1.  There is no network, so no real corpus."""
+    rng = np.random.default_rng(seed)
+    ranks = np.arange(1, vocab + 1, dtype=np.float64)
+    p = ranks ** (-exponent)
+    cdf = np.cumsum(p / p.sum())
+    ids = np.searchsorted(cdf, rng.random(n_tokens), side="right").astype(np.int32)
+    np.minimum(ids, vocab - 1, out=ids)
+    if sentence_len > 0:
+        ids[sentence_len::sentence_len + 1] = -1
+    return ids

@@ -1,0 +1,619 @@
+"""HBM-resident distributed tables (device backend).
+
+Reference layer L3/L4: WorkerTable / ServerTable (include/multiverso/table_interface.h:24-75,
+src/table.cpp), ArrayWorker/ArrayServer (src/table/array_table.cpp), MatrixWorkerTable /
+MatrixServerTable (src/table/matrix_table.cpp), MatrixWorker/MatrixServer with sparse
+delta-pull (src/table/matrix.cpp), SparseMatrixTable (src/table/sparse_matrix_table.cpp),
+KVWorkerTable/KVServerTable (include/multiverso/table/kv_table.h).
+
+B200 design: every rank holds its shard (and updater state) in a symmetric, peer-mapped
+HBM slab.  There is no worker half / server half exchanging messages:
+
+* ``add`` (whole table, BSP or stateful):  K1 ``mvb_add_dense_fused`` -- the owner pulls its
+  slice of every worker's staging buffer over NVLink and applies the updater in registers;
+  the ready/done "messages" are signal-pad flags handled inside the kernel.
+* ``add`` (async + stateless updater): one-sided ``red.global.add`` push into the owners.
+* ``get`` (whole): K2 pull all-gather straight from the owners' shards.
+* row ops: K4 gather / K3 scatter-add through the peer mappings.
+* handles: ``*_async`` returns an int id backed by a CUDA event; ``wait(id)`` synchronises it
+  (multiple Gets may be in flight; ids are recycled, Q7).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .. import _native as N
+from ..runtime import Runtime
+from ..utils import FLAGS, Log, monitor
+from .options import AddOption, GetOption
+
+_DT = {"float32": torch.float32, "float": torch.float32, "float64": torch.float64,
+       "double": torch.float64, "int32": torch.int32, "int": torch.int32, "int64": torch.int64}
+
+
+def _torch_dtype(d):
+    return d if isinstance(d, torch.dtype) else _DT[str(d)]
+
+
+def _opt_struct(o: AddOption) -> N.AddOpt:
+    return N.AddOpt(o.worker_id, o.momentum, o.learning_rate, o.rho, o.lambda_)
+
+
+class _AsyncOps:
+    """msg-id -> CUDA event bookkeeping (WorkerTable::Wait/Reset/Notify, src/table.cpp:84-111)."""
+
+    def __init__(self):
+        self._events: Dict[int, torch.cuda.Event] = {}
+        self._next = 0
+
+    def _record(self) -> int:
+        ev = torch.cuda.Event()
+        ev.record()
+        i = self._next
+        self._next += 1
+        self._events[i] = ev
+        return i
+
+    def wait(self, handle: int) -> None:
+        ev = self._events.pop(handle, None)
+        if ev is not None:
+            ev.synchronize()
+        Runtime.get().check_watchdog()
+
+
+class DenseDeviceTable(_AsyncOps):
+    """Range-partitioned dense storage; base of ArrayTable and MatrixTable."""
+
+    def __init__(self, num_row: int, num_col: int, dtype="float32", updater: Optional[str] = None,
+                 init_value=None, min_value=None, max_value=None, seed: int = 1):
+        super().__init__()
+        rt = Runtime.get()
+        if not rt.started:
+            Log.fatal("MV_Init must be called before creating tables")
+        self.rt = rt
+        self.num_row, self.num_col = int(num_row), int(num_col)
+        self.size = self.num_row * self.num_col
+        self.dtype = _torch_dtype(dtype)
+        self.dcode = N.dtype_code(self.dtype)
+        self.esz = torch.empty((), dtype=self.dtype).element_size()
+        name = updater or str(FLAGS.get("updater_type"))
+        if self.dtype in (torch.int32, torch.int64):
+            name = "default"      # Updater<int> is always the plain add (updater.cpp:40-43)
+        if name not in N.UPDATER_NAMES:
+            Log.fatal("unknown updater_type '%s'", name)
+        self.updater_name = name
+        self.updater = N.UPDATER_NAMES[name]
+        self.sync = bool(FLAGS.get("sync"))
+        S = max(rt.num_servers(), 1)
+        W = max(rt.num_workers(), 1)
+        self.S, self.W = S, W
+        # ---- partition: contiguous row ranges, last server takes the remainder ------------
+        # (array_table.cpp:15-19, matrix_table.cpp:26-45; fewer rows than servers => one row
+        # per server for the first num_row servers)
+        if self.num_row >= S:
+            self.rps = self.num_row // S
+            self.row_lo = [s * self.rps for s in range(S)]
+            self.row_hi = [(s + 1) * self.rps for s in range(S)]
+            self.row_hi[-1] = self.num_row
+        else:
+            self.rps = 1
+            self.row_lo = [min(s, self.num_row) for s in range(S)]
+            self.row_hi = [min(s + 1, self.num_row) for s in range(S)]
+        self.offs = [lo * self.num_col for lo in self.row_lo]
+        self.lens = [(hi - lo) * self.num_col for lo, hi in zip(self.row_lo, self.row_hi)]
+        self.sid = rt.server_id()
+        self.my_len = self.lens[self.sid] if self.sid >= 0 else 0
+        self.my_off = self.offs[self.sid] if self.sid >= 0 else 0
+        # ---- storage ---------------------------------------------------------------------
+        self.shard_buf = rt.alloc_symm(max(self.my_len, 1) * self.esz)
+        self.shard = self.shard_buf.tensor(self.dtype, max(self.my_len, 1))[: self.my_len]
+        if min_value is not None and max_value is not None and self.my_len:
+            g = torch.Generator(device=rt.device)
+            g.manual_seed(seed + 7919 * max(self.sid, 0))
+            self.shard.uniform_(float(min_value), float(max_value), generator=g)
+        elif init_value is not None and self.my_len:
+            self.shard.fill_(init_value)
+        # server s's shard as seen from here (indexed by server id)
+        self.shard_ptrs = [self.shard_buf.ptrs[rt.server_id_to_rank(s)] for s in range(S)] \
+            if rt.num_servers() else [self.shard_buf.local_ptr]
+        nst, per_worker = {"default": (0, False), "sgd": (0, False), "momentum_sgd": (1, False),
+                           "adagrad": (1, True), "dcasgd": (1, True),
+                           "dcasgda": (2, True)}[name]
+        self.n_states, self.state_per_worker = nst, per_worker
+        self.state_stride = (self.my_len + 3) // 4 * 4
+        slab = self.state_stride * (W if per_worker else 1)
+        self.state = [torch.zeros(max(slab, 1), dtype=self.dtype, device=rt.device)
+                      for _ in range(nst)]
+        # collective path resources (lazy)
+        self._stage: List = []
+        self._stage_idx = 0
+        self.ch_ready = rt.new_channels(2)
+        self.ch_done = self.ch_ready + 1
+        self.add_epoch = 0
+        self._done_counter = rt.done_counter_ptr()
+        self._fin = torch.zeros(1, dtype=torch.int32, device=rt.device)
+        self._finished = False
+        self.table_id = rt.register_table(self)
+        rt.barrier()   # MV_CreateTable ends with a barrier (multiverso.h:35-41)
+
+    # ------------------------------------------------------------------ helpers
+    def _stage_buf(self):
+        if not self._stage:
+            self._stage = [self.rt.alloc_symm(self.size * self.esz) for _ in range(2)]
+        b = self._stage[self._stage_idx]
+        self._stage_idx ^= 1
+        return b
+
+    def staging(self) -> torch.Tensor:
+        """Zero-copy Add: write your delta into the returned full-size tensor, then call
+        ``add(staged=True)``; the fused kernel reads it in place over NVLink."""
+        self._cur_stage = self._stage_buf()
+        return self._cur_stage.tensor(self.dtype, self.size)
+
+    def _as_device(self, data) -> torch.Tensor:
+        t = torch.as_tensor(data)
+        if t.dtype != self.dtype:
+            t = t.to(self.dtype)
+        if t.device != self.rt.device:
+            t = t.to(self.rt.device, non_blocking=True)
+        return t.contiguous().view(-1)
+
+    def _collective(self) -> bool:
+        stateless = self.updater in (N.UPD_DEFAULT, N.UPD_SGD)
+        if self.rt.size == 1:
+            return True
+        if self.sync:
+            return True
+        return not (stateless and bool(FLAGS.get("async_one_sided")))
+
+    # ------------------------------------------------------------------ Add (whole table)
+    def add(self, delta=None, option: Optional[AddOption] = None, staged: bool = False) -> None:
+        self.wait(self.add_async(delta, option, staged))
+
+    def add_async(self, delta=None, option: Optional[AddOption] = None, staged: bool = False) -> int:
+        rt, lib = self.rt, N.cuda_lib()
+        opt = option or AddOption()
+        nbytes = self.size * self.esz
+        with monitor("WORKER_TABLE_ADD", cuda=True, nbytes=nbytes):
+            if rt.size == 1:
+                src = self._cur_stage.tensor(self.dtype, self.size) if staged else self._as_device(delta)
+                self._launch_fused([src.data_ptr()], [opt], pads=False)
+                self._keep = src
+            elif self._collective():
+                if not staged:
+                    buf = self._stage_buf()
+                    if rt.is_worker():
+                        buf.tensor(self.dtype, self.size).copy_(self._as_device(delta))
+                else:
+                    buf = self._cur_stage
+                opts = [opt] * self.W
+                # per-worker options travel with the request in the reference; here every
+                # worker's option is its own -- gather the 20-byte structs once per call only
+                # when a stateful updater needs per-worker learning rates.
+                ptrs = [buf.ptrs[rt.worker_id_to_rank(w)] for w in range(self.W)]
+                self._launch_fused(ptrs, opts, pads=True)
+            else:
+                src = self._as_device(delta)
+                sign = -1.0 if self.updater == N.UPD_SGD else 1.0
+                sp = (C.c_void_p * self.S)(*self.shard_ptrs)
+                so = (C.c_int64 * self.S)(*self.offs)
+                sl = (C.c_int64 * self.S)(*self.lens)
+                N.check(lib.mvb_push_dense_red(self.dcode, C.c_void_p(src.data_ptr()), self.S, sp, so,
+                                               sl, C.c_float(sign), C.c_void_p(N.stream_ptr())),
+                        "mvb_push_dense_red")
+                self._keep = src
+        return self._record()
+
+    def _launch_fused(self, delta_ptrs: Sequence[int], opts: Sequence[AddOption], pads: bool,
+                      serve_only: bool = False) -> None:
+        rt, lib = self.rt, N.cuda_lib()
+        a = N.DenseAdd()
+        a.dtype, a.updater = self.dcode, self.updater
+        a.shard = self.shard_buf.local_ptr
+        a.state0 = self.state[0].data_ptr() if self.n_states >= 1 else None
+        a.state1 = self.state[1].data_ptr() if self.n_states >= 2 else None
+        a.shard_len, a.shard_off, a.state_stride = self.my_len, self.my_off, self.state_stride
+        nw = len(delta_ptrs)
+        a.nworkers = nw
+        a.worker_mask = (1 << nw) - 1
+        for w in range(nw):
+            a.delta_ptrs[w] = delta_ptrs[w]
+            a.opts[w] = _opt_struct(opts[w])
+            a.opts[w].worker_id = w
+            a.worker_rank[w] = rt.worker_id_to_rank(w) if rt.size > 1 else 0
+        a.scale, a.clip = 1.0, 0.0
+        self._pads_arr = rt.pads_array() if pads else None
+        a.pads = C.cast(self._pads_arr, C.POINTER(C.c_void_p)) if pads else None
+        a.me, a.world = rt.rank, rt.size
+        a.ch_ready, a.ch_done = self.ch_ready, self.ch_done
+        if pads:
+            self.add_epoch += 1
+        a.epoch = self.add_epoch
+        a.is_worker = 1 if (rt.is_worker() and not serve_only and not self._finished) else 0
+        a.err_flag = rt.err_flag.data_ptr()
+        a.fin_flag = self._fin.data_ptr()
+        a.done_counter = self._done_counter
+        a.timeout_s = float(FLAGS.get("barrier_timeout_s"))
+        N.check(lib.mvb_add_dense_fused(C.byref(a), C.c_void_p(N.stream_ptr())), "mvb_add_dense_fused")
+
+    # ------------------------------------------------------------------ Get (whole table)
+    def get(self, out: Optional[torch.Tensor] = None, option: Optional[GetOption] = None) -> torch.Tensor:
+        h, out = self._get_async(out)
+        self.wait(h)
+        return out
+
+    def get_async(self, out: Optional[torch.Tensor] = None, option: Optional[GetOption] = None):
+        return self._get_async(out)
+
+    def _get_async(self, out):
+        rt, lib = self.rt, N.cuda_lib()
+        if out is None:
+            out = torch.empty(self.size, dtype=self.dtype, device=rt.device)
+        flat = out.view(-1)
+        assert flat.numel() == self.size and flat.dtype == self.dtype and flat.is_cuda
+        g = N.DenseGet()
+        g.dtype, g.out, g.nservers = self.dcode, flat.data_ptr(), self.S
+        for s in range(self.S):
+            g.shard_ptrs[s] = self.shard_ptrs[s]
+            g.shard_offs[s] = self.offs[s]
+            g.shard_lens[s] = self.lens[s]
+            g.server_rank[s] = rt.server_id_to_rank(s) if rt.size > 1 else 0
+        use_pads = rt.size > 1 and self._collective() and self.add_epoch > 0
+        self._gpads = rt.pads_array() if use_pads else None
+        g.pads = C.cast(self._gpads, C.POINTER(C.c_void_p)) if use_pads else None
+        g.me, g.world, g.ch_done, g.epoch = rt.rank, rt.size, self.ch_done, self.add_epoch
+        g.err_flag = rt.err_flag.data_ptr()
+        g.timeout_s = float(FLAGS.get("barrier_timeout_s"))
+        with monitor("WORKER_TABLE_GET", cuda=True, nbytes=self.size * self.esz):
+            N.check(lib.mvb_get_dense(C.byref(g), C.c_void_p(N.stream_ptr())), "mvb_get_dense")
+        return self._record(), out
+
+    # ------------------------------------------------------------------ BSP shutdown
+    def finish_train(self) -> None:
+        """Server_Finish_Train: stop gating the BSP epochs on this worker and keep serving
+        the other workers' Adds until every worker has finished (src/zoo.cpp:152-161,
+        src/server.cpp:190-213)."""
+        rt = self.rt
+        if rt.size == 1 or not self.sync or self._finished or not self._stage:
+            self._finished = True
+            return
+        lib = N.cuda_lib()
+        self._finished = True
+        if rt.is_worker():
+            N.check(lib.mvb_signal(rt.pads_array(), rt.rank, rt.size, self.ch_ready,
+                                   C.c_uint64(N.EPOCH_FIN), C.c_void_p(N.stream_ptr())), "mvb_signal")
+        buf = self._stage[0]
+        ptrs = [buf.ptrs[rt.worker_id_to_rank(w)] for w in range(self.W)]
+        while True:
+            self._fin.zero_()
+            # staging parity must match what the still-running workers use for this epoch
+            buf = self._stage[self.add_epoch % 2]
+            ptrs = [buf.ptrs[rt.worker_id_to_rank(w)] for w in range(self.W)]
+            self._launch_fused(ptrs, [AddOption(0)] * self.W, pads=True, serve_only=True)
+            torch.cuda.current_stream().synchronize()
+            rt.check_watchdog()
+            if int(self._fin.item()):
+                break
+
+    def free(self) -> None:
+        for b in [self.shard_buf] + list(self._stage):
+            self.rt.release_symm(b)
+        self._stage = []
+        self.shard = None
+
+    # ------------------------------------------------------------------ checkpoint
+    def store(self, stream) -> None:
+        """Serializable::Store: raw dump of the local shard (array_table.cpp:143-151), followed
+        by the updater state slabs (not saved by the reference)."""
+        torch.cuda.current_stream().synchronize()
+        stream.write(self.shard.cpu().numpy().tobytes())
+        for st in self.state:
+            stream.write(st.cpu().numpy().tobytes())
+
+    def load(self, stream) -> None:
+        import numpy as np
+        npdt = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32,
+                torch.int64: np.int64}[self.dtype]
+        raw = stream.read(self.my_len * self.esz)
+        if self.my_len:
+            self.shard.copy_(torch.from_numpy(np.frombuffer(raw, dtype=npdt).copy()).to(self.rt.device))
+        for st in self.state:
+            raw = stream.read(st.numel() * self.esz)
+            if len(raw) == st.numel() * self.esz:
+                st.copy_(torch.from_numpy(np.frombuffer(raw, dtype=npdt).copy()).to(self.rt.device))
+
+
+class ArrayDeviceTable(DenseDeviceTable):
+    """ArrayTable<T>: dense 1-D, whole-table ops (any size >= 1)."""
+
+    def __init__(self, size: int, dtype="float32", updater=None, init_value=None):
+        super().__init__(int(size), 1, dtype, updater, init_value)
+
+
+class MatrixDeviceTable(DenseDeviceTable):
+    """MatrixTable<T> / Matrix<T> / SparseMatrixTable<T>: dense 2-D, row addressable.
+
+    ``is_sparse`` enables the reference's delta-pull protocol (src/table/matrix.cpp:421-572):
+    every Add marks the touched rows stale for all workers (T4 behaviour, Q13) and
+    ``get_stale()`` returns only the rows that changed since this worker's last pull; an
+    explicit empty result replaces the reference's row-0 placeholder (Q12).  Whole-table adds
+    skip all-zero rows when marking (matrix.cpp:151-164)."""
+
+    def __init__(self, num_row: int, num_col: int, dtype="float32", updater=None, init_value=None,
+                 min_value=None, max_value=None, is_sparse: bool = False, is_pipeline: bool = False,
+                 seed: int = 1):
+        self.is_sparse, self.is_pipeline = bool(is_sparse), bool(is_pipeline)
+        super().__init__(num_row, num_col, dtype, updater, init_value, min_value, max_value, seed)
+        rt = self.rt
+        self._rowmap = N.RowMap()
+        self._rowmap.num_row, self._rowmap.num_col = self.num_row, self.num_col
+        self._rowmap.nservers = self.S
+        self._rowmap.rows_per_server = self.rps
+        for s in range(self.S):
+            self._rowmap.shard_ptrs[s] = self.shard_ptrs[s]
+        self._stale = None
+        if self.is_sparse:
+            nslots = self.W * (2 if self.is_pipeline else 1)
+            # the stale bitmap is replicated: each rank tracks rows it has itself seen change
+            # through Adds issued anywhere (marks are pushed by the adder to every rank's copy)
+            self._stale_buf = rt.alloc_symm(nslots * self.num_row)
+            self._stale = self._stale_buf.tensor(torch.uint8, nslots * self.num_row)
+            self._stale.fill_(1)           # everything is stale before the first Get
+            self._nslots = nslots
+            rt.barrier()
+
+    # ---- ids helper --------------------------------------------------------------------
+    def _ids(self, row_ids) -> torch.Tensor:
+        t = torch.as_tensor(row_ids)
+        if t.dtype != torch.int64:
+            t = t.to(torch.int64)
+        if t.device != self.rt.device:
+            t = t.to(self.rt.device, non_blocking=True)
+        return t.contiguous().view(-1)
+
+    # ---- row Get -----------------------------------------------------------------------
+    def get_rows(self, row_ids, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        h, out = self.get_rows_async(row_ids, out)
+        self.wait(h)
+        return out
+
+    def get_rows_async(self, row_ids, out: Optional[torch.Tensor] = None):
+        lib = N.cuda_lib()
+        ids = self._ids(row_ids)
+        k = ids.numel()
+        if out is None:
+            out = torch.empty(k, self.num_col, dtype=self.dtype, device=self.rt.device)
+        assert out.is_cuda and out.dtype == self.dtype and out.stride(-1) == 1
+        ld = out.stride(0) if out.dim() == 2 else self.num_col
+        with monitor("WORKER_TABLE_GET_ROWS", cuda=True, nbytes=k * self.num_col * self.esz):
+            N.check(lib.mvb_get_rows(self.dcode, C.byref(self._rowmap), C.c_void_p(ids.data_ptr()),
+                                     C.c_int64(k), C.c_void_p(out.data_ptr()), C.c_int64(ld),
+                                     C.c_void_p(N.stream_ptr())), "mvb_get_rows")
+        self._keep_ids = ids
+        return self._record(), out
+
+    def get_row(self, row_id: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.get_rows([row_id], None if out is None else out.view(1, -1)).view(-1)
+
+    # ---- row Add -----------------------------------------------------------------------
+    def add_rows(self, row_ids, values, option: Optional[AddOption] = None) -> None:
+        self.wait(self.add_rows_async(row_ids, values, option))
+
+    def add_rows_async(self, row_ids, values, option: Optional[AddOption] = None) -> int:
+        rt, lib = self.rt, N.cuda_lib()
+        ids = self._ids(row_ids)
+        k = ids.numel()
+        vals = torch.as_tensor(values)
+        if vals.dtype != self.dtype:
+            vals = vals.to(self.dtype)
+        if vals.device != rt.device:
+            vals = vals.to(rt.device, non_blocking=True)
+        vals = vals.contiguous().view(k, self.num_col)
+        opt = option or AddOption()
+        st = C.c_void_p(N.stream_ptr())
+        with monitor("WORKER_TABLE_ADD_ROWS", cuda=True, nbytes=k * self.num_col * self.esz):
+            if self.updater in (N.UPD_DEFAULT, N.UPD_SGD):
+                sign = -1.0 if self.updater == N.UPD_SGD else 1.0
+                N.check(lib.mvb_add_rows_red(self.dcode, C.byref(self._rowmap),
+                                             C.c_void_p(ids.data_ptr()), C.c_int64(k),
+                                             C.c_void_p(vals.data_ptr()), C.c_int64(self.num_col),
+                                             C.c_float(sign), st), "mvb_add_rows_red")
+            else:
+                self._add_rows_stateful(ids, vals, opt)
+            if self.is_sparse:
+                self._mark_stale(ids)
+        self._keep_rows = (ids, vals)
+        return self._record()
+
+    def add_row(self, row_id: int, values, option: Optional[AddOption] = None) -> None:
+        self.add_rows([row_id], torch.as_tensor(values).view(1, -1), option)
+
+    def _add_rows_stateful(self, ids, vals, opt: AddOption) -> None:
+        """Stateful updaters must be applied by the owner exactly once per (worker,row): the
+        request (ids, values) is published in symmetric staging, every owner scans all
+        workers' requests in worker order (collective, like the dense fused path)."""
+        rt, lib = self.rt, N.cuda_lib()
+        k = ids.numel()
+        st = C.c_void_p(N.stream_ptr())
+        ao = _opt_struct(opt)
+        if rt.size == 1:
+            ao.worker_id = 0
+            N.check(lib.mvb_add_rows_owner(self.dcode, self.updater, C.c_void_p(self.shard_buf.local_ptr),
+                                           self._sp(0), self._sp(1), C.c_int64(self.row_lo[0]),
+                                           C.c_int64(self.row_hi[0]), C.c_int64(self.num_col),
+                                           C.c_int64(self.state_stride), C.c_void_p(ids.data_ptr()),
+                                           C.c_int64(k), C.c_void_p(vals.data_ptr()),
+                                           C.c_int64(self.num_col), C.byref(ao), st), "mvb_add_rows_owner")
+            return
+        counts = rt.all_gather_object(int(k))
+        cap = max(max(counts), 1)
+        if getattr(self, "_row_stage_cap", 0) < cap:
+            self._row_stage_ids = rt.alloc_symm(cap * 8)
+            self._row_stage_vals = rt.alloc_symm(cap * self.num_col * self.esz)
+            self._row_stage_cap = cap
+        else:
+            rt.barrier()   # previous round's readers are done before we overwrite staging
+        if k:
+            self._row_stage_ids.tensor(torch.int64, k).copy_(ids)
+            self._row_stage_vals.tensor(self.dtype, k * self.num_col).copy_(vals.view(-1))
+        rt.barrier()
+        if self.sid >= 0:
+            for w in range(self.W):
+                r = rt.worker_id_to_rank(w)
+                if counts[r] == 0:
+                    continue
+                ao.worker_id = w
+                N.check(lib.mvb_add_rows_owner(
+                    self.dcode, self.updater, C.c_void_p(self.shard_buf.local_ptr), self._sp(0),
+                    self._sp(1), C.c_int64(self.row_lo[self.sid]), C.c_int64(self.row_hi[self.sid]),
+                    C.c_int64(self.num_col), C.c_int64(self.state_stride),
+                    C.c_void_p(self._row_stage_ids.ptrs[r]), C.c_int64(counts[r]),
+                    C.c_void_p(self._row_stage_vals.ptrs[r]), C.c_int64(self.num_col), C.byref(ao), st),
+                    "mvb_add_rows_owner")
+        rt.barrier()
+
+    def _sp(self, i):
+        return C.c_void_p(self.state[i].data_ptr()) if self.n_states > i else C.c_void_p(0)
+
+    # ---- whole-table ops honour the sparse bookkeeping ----------------------------------
+    def add_async(self, delta=None, option=None, staged=False) -> int:
+        if self.is_sparse and not staged and delta is not None:
+            lib = N.cuda_lib()
+            d = self._as_device(delta)
+            mask = torch.empty(self.num_row, dtype=torch.uint8, device=self.rt.device)
+            N.check(lib.mvb_row_nonzero_mask(self.dcode, C.c_void_p(d.data_ptr()), C.c_int64(self.num_row),
+                                             C.c_int64(self.num_col), C.c_int64(self.num_col),
+                                             C.c_void_p(mask.data_ptr()), C.c_void_p(N.stream_ptr())),
+                    "mvb_row_nonzero_mask")
+            h = super().add_async(d, option, False)
+            self._mark_stale(mask.nonzero().view(-1))
+            return h
+        return super().add_async(delta, option, staged)
+
+    def _mark_stale(self, ids: torch.Tensor) -> None:
+        lib = N.cuda_lib()
+        k = ids.numel()
+        if k == 0:
+            return
+        for r in range(self.rt.size):
+            N.check(lib.mvb_stale_mark(C.c_void_p(self._stale_buf.ptrs[r]), C.c_int64(self.num_row),
+                                       self._nslots, C.c_void_p(ids.data_ptr()), C.c_int64(k),
+                                       C.c_void_p(N.stream_ptr())), "mvb_stale_mark")
+        self._keep_mark = ids
+
+    def get_stale(self, option: Optional[GetOption] = None, slot: int = 0):
+        """Delta pull: (row_ids, rows) that changed since this worker's previous pull.
+        ``option.worker_id == -1`` returns every row (matrix.cpp:460-514)."""
+        lib = N.cuda_lib()
+        wid = (option.worker_id if option else self.rt.worker_id())
+        if not self.is_sparse or wid < 0:
+            ids = torch.arange(self.num_row, device=self.rt.device)
+            return ids, self.get_rows(ids)
+        w = wid + (self.W if (self.is_pipeline and slot) else 0)
+        mine = self._stale[w * self.num_row:(w + 1) * self.num_row]
+        mask = torch.empty(self.num_row, dtype=torch.uint8, device=self.rt.device)
+        N.check(lib.mvb_stale_take(C.c_void_p(mine.data_ptr()), C.c_int64(self.num_row), None,
+                                   C.c_int64(-1), C.c_void_p(mask.data_ptr()),
+                                   C.c_void_p(N.stream_ptr())), "mvb_stale_take")
+        ids = mask.nonzero().view(-1)
+        if ids.numel() == 0:
+            return ids, torch.empty(0, self.num_col, dtype=self.dtype, device=self.rt.device)
+        return ids, self.get_rows(ids)
+
+
+class KVDeviceTable(_AsyncOps):
+    """KVTable<K,V>: hash-partitioned map (key % num_servers) as per-shard GPU hash tables.
+
+    ``raw()`` exposes the worker-side cache dict like the reference (kv_table.h:30)."""
+
+    def __init__(self, key_dtype="int64", val_dtype="float32", capacity: Optional[int] = None):
+        super().__init__()
+        rt = Runtime.get()
+        self.rt = rt
+        self.vdtype = _torch_dtype(val_dtype)
+        self.vcode = N.dtype_code(self.vdtype)
+        self.vsz = torch.empty((), dtype=self.vdtype).element_size()
+        cap = int(capacity or FLAGS.get("kv_capacity"))
+        cap = 1 << (cap - 1).bit_length()
+        self.capacity = cap
+        self.S = max(rt.num_servers(), 1)
+        self.keys_buf = rt.alloc_symm(cap * 8)
+        self.vals_buf = rt.alloc_symm(cap * self.vsz)
+        lib = N.cuda_lib()
+        N.check(lib.mvb_kv_init(C.c_void_p(self.keys_buf.local_ptr), C.c_int64(cap),
+                                C.c_void_p(N.stream_ptr())), "mvb_kv_init")
+        self._kv = N.KV()
+        self._kv.vtype, self._kv.nservers, self._kv.capacity = self.vcode, self.S, cap
+        for s in range(self.S):
+            r = rt.server_id_to_rank(s) if rt.num_servers() else rt.rank
+            self._kv.keys[s] = self.keys_buf.ptrs[r]
+            self._kv.vals[s] = self.vals_buf.ptrs[r]
+        self._cache: Dict[int, object] = {}
+        self.table_id = rt.register_table(self)
+        rt.barrier()
+
+    def raw(self) -> Dict[int, object]:
+        return self._cache
+
+    def _keys(self, keys) -> torch.Tensor:
+        t = torch.as_tensor(keys, dtype=torch.int64)
+        return t.to(self.rt.device).contiguous().view(-1)
+
+    def add(self, keys, vals) -> None:
+        lib = N.cuda_lib()
+        scalar = not hasattr(keys, "__len__") and not torch.is_tensor(keys)
+        k = self._keys([keys] if scalar else keys)
+        v = torch.as_tensor([vals] if scalar else vals).to(self.vdtype).to(self.rt.device).contiguous().view(-1)
+        assert k.numel() == v.numel()
+        N.check(lib.mvb_kv_add(C.byref(self._kv), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()),
+                               C.c_int64(k.numel()), C.c_void_p(self.rt.err_flag.data_ptr()),
+                               C.c_void_p(N.stream_ptr())), "mvb_kv_add")
+        torch.cuda.current_stream().synchronize()
+        self.rt.check_watchdog()
+
+    def get(self, keys):
+        lib = N.cuda_lib()
+        scalar = not hasattr(keys, "__len__") and not torch.is_tensor(keys)
+        k = self._keys([keys] if scalar else keys)
+        out = torch.empty(k.numel(), dtype=self.vdtype, device=self.rt.device)
+        N.check(lib.mvb_kv_get(C.byref(self._kv), C.c_void_p(k.data_ptr()), C.c_void_p(out.data_ptr()),
+                               C.c_int64(k.numel()), C.c_void_p(N.stream_ptr())), "mvb_kv_get")
+        host = out.cpu()
+        for kk, vv in zip(k.cpu().tolist(), host.tolist()):
+            self._cache[kk] = vv
+        return host[0].item() if scalar else out
+
+    def free(self) -> None:
+        self.rt.release_symm(self.keys_buf)
+        self.rt.release_symm(self.vals_buf)
+
+    def store(self, stream) -> None:
+        """KV checkpoint (the reference's is Fatal("Not implemented"), kv_table.h:108-114)."""
+        import struct
+        lib = N.cuda_lib()
+        ok = torch.empty(self.capacity, dtype=torch.int64, device=self.rt.device)
+        ov = torch.empty(self.capacity, dtype=self.vdtype, device=self.rt.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.rt.device)
+        N.check(lib.mvb_kv_dump(self.vcode, C.c_void_p(self.keys_buf.local_ptr),
+                                C.c_void_p(self.vals_buf.local_ptr), C.c_int64(self.capacity),
+                                C.c_void_p(ok.data_ptr()), C.c_void_p(ov.data_ptr()),
+                                C.c_void_p(cnt.data_ptr()), C.c_void_p(N.stream_ptr())), "mvb_kv_dump")
+        n = int(cnt.item())
+        stream.write(struct.pack("<q", n))
+        stream.write(ok[:n].cpu().numpy().tobytes())
+        stream.write(ov[:n].cpu().numpy().tobytes())
+
+    def load(self, stream) -> None:
+        import struct
+        import numpy as np
+        (n,) = struct.unpack("<q", stream.read(8))
+        if n == 0:
+            return
+        keys = np.frombuffer(stream.read(8 * n), dtype=np.int64).copy()
+        npdt = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32,
+                torch.int64: np.int64}[self.vdtype]
+        vals = np.frombuffer(stream.read(self.vsz * n), dtype=npdt).copy()
+        self.add(torch.from_numpy(keys), torch.from_numpy(vals))

@@ -1,0 +1,159 @@
+"""Multi-GPU end-to-end checks, launched with torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/mp_device_check.py
+
+Mirrors the reference's multi-process scenarios (Test/test_array_table.cpp, test_matrix_table.cpp,
+test_kv_table.cpp, test_allreduce.cpp) with their exact integer expectations, on the device
+backend: fused BSP Add/Get (K1/K2), one-sided async push, row ops (K3/K4), KV (K5),
+allreduce (K6), uneven iteration counts + FinishTrain, and a distributed WordEmbedding block.
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import multiverso_b200 as mv
+
+results = {}
+
+
+def check(name, cond, info=""):
+    results[name] = bool(cond)
+    if not cond:
+        print(f"[rank {mv.rank()}] FAIL {name} {info}", flush=True)
+
+
+def scenario_sync():
+    mv.init(sync=True)
+    W, r = mv.num_workers(), mv.rank()
+    n = 1 << 20
+    t = mv.ArrayTable(n, "float32")
+    delta = torch.arange(n, dtype=torch.float32, device="cuda") % 1000 + 1
+    ok = True
+    for it in range(1, 6):
+        t.add(delta)
+        got = t.get()
+        ok &= bool(torch.equal(got, delta * it * W))
+    check("bsp_array_exact", ok)
+    # momentum updater: every owner applies the W deltas sequentially in worker order
+    tm = mv.ArrayTable(10007, "float32", updater="momentum_sgd")
+    d = torch.full((10007,), 1.0, device="cuda") * (r + 1)
+    opt = mv.AddOption(momentum=0.5)
+    tm.add(d, opt)
+    s, x = 0.0, 0.0
+    for w in range(W):
+        s = 0.5 * s + 0.5 * (w + 1)
+        x -= s
+    check("bsp_momentum_sequential", torch.allclose(tm.get(), torch.full((10007,), x, device="cuda")))
+    # matrix scenario (test_matrix_table.cpp): whole + rows 0,1,3,7
+    rows, cols = 1000, 64
+    m = mv.MatrixTable(rows, cols, "float32")
+    base = (torch.arange(rows * cols, dtype=torch.float32, device="cuda") % 97 + 1).view(rows, cols)
+    ids = torch.tensor([0, 1, 3, 7, 999], device="cuda")
+    ok = True
+    for count in range(1, 4):
+        m.add(base)
+        mv.barrier()
+        m.add_rows(ids, base[ids])
+        mv.barrier()
+        exp = base * count * W
+        exp[ids] *= 2
+        ok &= bool(torch.equal(m.get().view(rows, cols), exp))
+        ok &= bool(torch.equal(m.get_rows(ids), exp[ids]))
+        mv.barrier()
+    check("bsp_matrix_rows_exact", ok)
+    # uneven iteration counts (test_array_table.cpp:30) -> FinishTrain on shutdown
+    tu = mv.ArrayTable(4096, "float32")
+    one = torch.ones(4096, device="cuda")
+    iters = 3 + r
+    for it in range(iters):
+        tu.add(one)
+        tu.get()
+    mv.shutdown(finalize_net=False)
+    check("bsp_uneven_finish_train", True)
+
+
+def scenario_async():
+    mv.init(sync=False)
+    W, r = mv.num_workers(), mv.rank()
+    n = 300007
+    t = mv.ArrayTable(n, "float32")            # default updater -> one-sided red.add push
+    delta = torch.arange(n, dtype=torch.float32, device="cuda") % 13 + 1
+    for it in range(4):
+        t.add(delta)
+    mv.barrier()
+    check("async_push_red_exact", torch.equal(t.get(), delta * 4 * W))
+    ts = mv.ArrayTable(n, "float32", updater="sgd")
+    ts.add(delta)
+    mv.barrier()
+    check("async_sgd_sign", torch.equal(ts.get(), -delta * W))
+    # rows
+    m = mv.MatrixTable(5000, 300, "float32")
+    ids = torch.arange(r, 5000, 7, device="cuda")
+    vals = torch.ones(ids.numel(), 300, device="cuda") * (r + 1)
+    m.add_rows(ids, vals)
+    mv.barrier()
+    full = m.get().view(5000, 300)
+    exp = torch.zeros(5000, 300, device="cuda")
+    for w in range(W):
+        exp[torch.arange(w, 5000, 7, device="cuda")] += (w + 1)
+    check("async_rows_scatter_add", torch.equal(full, exp))
+    check("rows_gather", torch.equal(m.get_rows(ids), exp[ids]))
+    # stateful rows: owner-applied, exactly once per (worker,row)
+    ma = mv.MatrixTable(512, 32, "float32", updater="adagrad")
+    rid = torch.arange(0, 512, 3, device="cuda")
+    ma.add_rows(rid, torch.ones(rid.numel(), 32, device="cuda") * 0.01, mv.AddOption(learning_rate=0.01, rho=0.1))
+    got = ma.get().view(512, 32)
+    # each worker has its own G^2 history: g=1, G2=1 -> step = rho/sqrt(1+1e-6)
+    check("stateful_rows_adagrad", torch.allclose(got[rid], torch.full((rid.numel(), 32), -0.1 * W, device="cuda"), atol=1e-4))
+    # KV
+    kv = mv.KVTable("int64", "float32")
+    keys = torch.arange(0, 1000, device="cuda")
+    kv.add(keys, torch.ones(1000, device="cuda"))
+    mv.barrier()
+    check("kv_add_get", torch.equal(kv.get(keys), torch.full((1000,), float(W), device="cuda")))
+    # allreduce (test_allreduce.cpp): sum of ones == size; plus large two-shot
+    x = torch.ones(1, dtype=torch.int32, device="cuda")
+    mv.aggregate(x)
+    check("aggregate_int", int(x.item()) == mv.size())
+    for n_el in (1000, 3_000_001):
+        y = torch.full((n_el,), float(r + 1), device="cuda")
+        mv.aggregate(y)
+        check(f"aggregate_f32_{n_el}", torch.equal(y, torch.full((n_el,), W * (W + 1) / 2.0, device="cuda")))
+    # distributed WordEmbedding block (block mode)
+    from multiverso_b200.models.wordembedding import WordEmbedding, WordEmbeddingOption, synthetic_zipf_corpus
+    we = WordEmbedding(WordEmbeddingOption(embeding_size=300, init_learning_rate=0.05), 50000)
+    toks = torch.from_numpy(synthetic_zipf_corpus(200000, 50000, 1000, seed=r)).cuda()
+    losses = []
+    for it in range(4):
+        we.loss.zero_(); we.pairs.zero_()
+        we.train_block(toks)
+        torch.cuda.synchronize()
+        losses.append(float(we.loss.item()) / max(int(we.pairs.item()), 1))
+    mv.barrier()
+    check("wordembedding_block_mode", losses[-1] < losses[0] and all(l == l for l in losses), str(losses))
+    mv.shutdown()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    t0 = time.time()
+    try:
+        if which in ("all", "sync"):
+            scenario_sync()
+        if which in ("all", "async"):
+            scenario_async()
+    except Exception as e:
+        import traceback
+        traceback.print_exc()
+        results["exception"] = False
+    rank = int(os.environ.get("RANK", "0"))
+    ok = all(results.values()) and len(results) > 0
+    print(f"[rank {rank}] {'PASS' if ok else 'FAIL'} {json.dumps(results)} ({time.time() - t0:.1f}s)", flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/mp_check_rank{rank}.json", "w") as f:
+        json.dump(results, f)
+    sys.exit(0 if ok else 1)

@@ -1,0 +1,170 @@
+"""GPU numerics: every table kernel against a plain PyTorch fp32/fp64 reference.
+Scenarios mirror Test/unittests/test_array.cpp, test_kv.cpp, Test/test_matrix_table.cpp."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_update(name, data, delta, st, opt):
+    m, lr, rho, lam = opt["momentum"], opt["lr"], opt["rho"], opt["lam"]
+    if name == "default":
+        data += delta
+    elif name == "sgd":
+        data -= delta
+    elif name == "momentum_sgd":
+        st[0].mul_(m).add_((1 - m) * delta)
+        data -= st[0]
+    elif name == "adagrad":
+        g = delta / lr
+        st[0] += g * g
+        data -= rho / torch.sqrt(st[0] + 1e-6) * g
+    elif name == "dcasgd":
+        g = delta / lr
+        data -= lr * (g + lam * g * g * (data - st[0]))
+        st[0].copy_(data)
+    elif name == "dcasgda":
+        g = delta / lr
+        st[1].mul_(m).add_((1 - m) * g * g)
+        data -= lr * (g + lam / torch.sqrt(st[1] + 1e-7) * g * g * (data - st[0]))
+        st[0].copy_(data)
+
+
+@pytest.mark.parametrize("updater", ["default", "sgd", "momentum_sgd", "adagrad", "dcasgd", "dcasgda"])
+@pytest.mark.parametrize("size", [1, 1000, 4099, 1 << 20])
+def test_array_add_get_matches_reference(mv_device, updater, size):
+    mv = mv_device
+    t = mv.ArrayTable(size, "float32", updater=updater)
+    torch.manual_seed(0)
+    ref = torch.zeros(size, dtype=torch.float64)
+    st = [torch.zeros(size, dtype=torch.float64), torch.zeros(size, dtype=torch.float64)]
+    opt = mv.AddOption(momentum=0.9, learning_rate=0.05, rho=0.1, lambda_=0.2)
+    o = dict(momentum=0.9, lr=0.05, rho=0.1, lam=0.2)
+    for it in range(3):
+        delta = torch.randn(size, device="cuda") * 0.1
+        t.add(delta, opt)
+        _ref_update(updater, ref, delta.double().cpu(), st, o)
+    got = t.get().cpu().double()
+    assert torch.allclose(got, ref, rtol=2e-4, atol=2e-5), (got - ref).abs().max()
+
+
+def test_array_integer_scenario_exact(mv_device):
+    """test_array.cpp:26-44: Add(delta) -> Get == delta; AddAsync+GetAsync+Wait == 2*delta."""
+    mv = mv_device
+    n = 100000
+    t = mv.ArrayTable(n, "float32")
+    delta = torch.arange(n, dtype=torch.float32, device="cuda")
+    t.add(delta)
+    assert torch.equal(t.get(), delta)
+    h = t.add_async(delta)
+    t.wait(h)
+    h2, out = t.get_async()
+    t.wait(h2)
+    assert torch.equal(out, 2 * delta)
+    ti = mv.ArrayTable(1001, "int32")
+    di = torch.arange(1001, dtype=torch.int32, device="cuda")
+    ti.add(di)
+    ti.add(di)
+    assert torch.equal(ti.get(), 2 * di)
+    td = mv.ArrayTable(513, "float64", updater="sgd")
+    dd = torch.randn(513, dtype=torch.float64, device="cuda")
+    td.add(dd)
+    assert torch.allclose(td.get(), -dd)
+
+
+def test_matrix_rows_exact_integer_scenario(mv_device):
+    """Test/test_matrix_table.cpp:9-99 at world size 1: whole-table and row-set Add/Get with
+    the exact integer expectation (i*cols+j+1)*count (doubled for rows 0,1,3,7)."""
+    mv = mv_device
+    rows, cols = 11, 10
+    t = mv.MatrixTable(rows, cols, "float32")
+    base = (torch.arange(rows * cols, dtype=torch.float32, device="cuda") + 1).view(rows, cols)
+    ids = torch.tensor([0, 1, 3, 7], device="cuda")
+    for count in range(1, 4):
+        t.add(base)
+        t.add_rows(ids, base[ids])
+        got = t.get().view(rows, cols)
+        exp = base * count
+        exp[ids] *= 2
+        assert torch.equal(got, exp)
+        assert torch.equal(t.get_rows(ids), exp[ids])
+        assert torch.equal(t.get_row(5), exp[5])
+
+
+@pytest.mark.parametrize("cols", [1, 7, 300, 512])
+def test_matrix_get_add_rows_random(mv_device, cols):
+    mv = mv_device
+    rows = 5000
+    t = mv.MatrixTable(rows, cols, "float32", min_value=-1.0, max_value=1.0)
+    full = t.get().view(rows, cols).clone()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ids = torch.randperm(rows, device="cuda", generator=g)[:777]
+    assert torch.equal(t.get_rows(ids), full[ids])
+    vals = torch.randn(777, cols, device="cuda")
+    t.add_rows(ids, vals)
+    full[ids] += vals
+    assert torch.allclose(t.get().view(rows, cols), full, atol=1e-6)
+
+
+def test_matrix_stateful_rows_and_sparse_stale(mv_device):
+    mv = mv_device
+    rows, cols = 64, 16
+    t = mv.MatrixTable(rows, cols, "float32", updater="momentum_sgd", is_sparse=True)
+    ids0, r0 = t.get_stale()
+    assert ids0.numel() == rows           # everything stale before the first pull
+    ids1, _ = t.get_stale()
+    assert ids1.numel() == 0              # explicit empty result (Q12)
+    ids = torch.tensor([3, 9, 40], device="cuda")
+    vals = torch.ones(3, cols, device="cuda")
+    opt = mv.AddOption(momentum=0.5)
+    t.add_rows(ids, vals, opt)
+    sid, srows = t.get_stale()
+    assert sid.tolist() == [3, 9, 40]
+    assert torch.allclose(srows, torch.full((3, cols), -0.5, device="cuda"))
+    d = torch.zeros(rows, cols, device="cuda")
+    d[5] = 2.0
+    t.add(d, opt)                          # zero rows are skipped when marking
+    sid, _ = t.get_stale()
+    assert sid.tolist() == [5]
+
+
+def test_kv_table(mv_device):
+    """test_kv.cpp:25-39: Get 0 -> 0, Add 3 -> 3, Add -4 -> -1."""
+    mv = mv_device
+    kv = mv.KVTable("int64", "float32")
+    assert kv.get(0) == 0
+    kv.add(0, 3.0)
+    assert kv.get(0) == 3.0
+    kv.add(0, -4.0)
+    assert kv.get(0) == -1.0
+    keys = torch.arange(-500, 500, device="cuda") * 7919
+    kv.add(keys, torch.ones(1000, device="cuda"))
+    kv.add(keys, torch.ones(1000, device="cuda"))
+    assert torch.equal(kv.get(keys), torch.full((1000,), 2.0, device="cuda"))
+    assert kv.raw()[0] == -1.0
+    kvi = mv.KVTable("int64", "int64")
+    kvi.add(4, 10**12)
+    kvi.add(4, 5)
+    assert kvi.get(4) == 10**12 + 5
+
+
+def test_aggregate_single_rank(mv_device):
+    x = torch.ones(10, device="cuda")
+    mv_device.aggregate(x)
+    assert torch.equal(x, torch.ones(10, device="cuda"))
+
+
+def test_checkpoint_roundtrip(mv_device, tmp_path):
+    import io
+    mv = mv_device
+    t = mv.ArrayTable(1000, "float32", updater="momentum_sgd")
+    t.add(torch.randn(1000, device="cuda"), mv.AddOption(momentum=0.9))
+    buf = io.BytesIO()
+    t.store(buf)
+    want = t.get().clone()
+    t2 = mv.ArrayTable(1000, "float32", updater="momentum_sgd")
+    buf.seek(0)
+    t2.load(buf)
+    assert torch.equal(t2.get(), want)
+    assert torch.equal(t2.state[0], t.state[0])

@@ -1,0 +1,46 @@
+#!/bin/bash
+# One gpurun call = everything we want from a box. Usage: tools/gpu_suite.sh [NGPU] [stage...]
+# Output goes to gpurun_out/ (merged back into the repo by gpurun).
+NG=${1:-1}; shift
+STAGES=${@:-"info test smoke bench mp ncu"}
+mkdir -p gpurun_out
+export MVB200_NO_BUILD=1
+PORT=29511
+for s in $STAGES; do
+case $s in
+info)
+  nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/info.txt 2>&1
+  nvidia-smi topo -m >> gpurun_out/info.txt 2>&1
+  ;;
+test)
+  timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+  tail -15 gpurun_out/pytest_gpu.log
+  ;;
+smoke)
+  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
+  ;;
+bench)
+  timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
+  ;;
+mp)
+  if [ "$NG" -gt 1 ]; then
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $PORT tests/mp_device_check.py > gpurun_out/mp_check.log 2>&1; echo "mp rc=$?"; grep -E "PASS|FAIL|Error|error" gpurun_out/mp_check.log | head -20
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+1)) bench.py --gpus $NG --steps 10 --warmup 3 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err; echo "bench$NG rc=$?"; cat gpurun_out/bench_n$NG.json; tail -5 gpurun_out/bench_n$NG.err
+  fi
+  ;;
+ncu)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgns_fast -s 3 -c 1 -f -o gpurun_out/sgns_fast python bench.py --steps 2 --warmup 3 --no-table-bw > gpurun_out/ncu_sgns.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/ncu_sgns.log
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; echo "launches rc=$?"
+  ;;
+ncu_dense)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"add_dense_fused|get_dense" -c 4 -f -o gpurun_out/dense python -c "
+import torch, multiverso_b200 as mv
+mv.init(); t = mv.MatrixTable(1000000, 512, 'float32', updater='sgd'); d = torch.ones(512000000, device='cuda')
+t.add(d); t.get(); t.add(d); t.get(); mv.shutdown()" > gpurun_out/ncu_dense.log 2>&1; echo "ncu_dense rc=$?"
+  ;;
+probe)
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+2)) tools/probe_symm.py > gpurun_out/probe.log 2>&1; echo "probe rc=$?"; tail -20 gpurun_out/probe.log
+  ;;
+esac
+done
+ls -la gpurun_out | head -40
