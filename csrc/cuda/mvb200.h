@@ -230,8 +230,10 @@ typedef struct MvbSgns {
   uint64_t seed;
   float* loss_sum;           /* optional: += sum of -log sigma(..)         */
   unsigned long long* pair_count;  /* optional: += trained (input,target) samples */
+  int variant;               /* kernel variant: 0 auto, 1..5 = negatives held in registers, 10 = TMA pipeline */
 } MvbSgns;
 int mvb_sgns_train(const MvbSgns* a, void* stream);
+int mvb_sgns_train_tma(const MvbSgns* a, void* stream);   /* TMA bulk-copy pipeline variant */
 int mvb_build_alias_table(const double* weights_host, int n, float* prob_host, int* alias_host);
 
 /* ---- LogisticRegression (K8) ---------------------------------------------------- */

@@ -16,6 +16,7 @@
 //   sgns_fast_kernel    : skip-gram + negative sampling, plain SGD, D % 4 == 0, D <= 512
 //   w2v_generic_kernel  : CBOW / hierarchical softmax / AdaGrad / any D (smem staged)
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "mvb_common.cuh"
 
@@ -135,8 +136,8 @@ MVB_DEVINL Row<VPL> row_zero() {
 }
 
 // KB = negatives whose rows are held in registers at once.
-template <int VPL, int KB>
-__global__ void __launch_bounds__(128)
+template <int VPL, int KB, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 sgns_fast_kernel(const __grid_constant__ SgnsDev a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -390,6 +391,8 @@ SgnsDev to_dev(const MvbSgns* h) {
 
 }  // namespace
 
+extern "C" int mvb_sgns_train_tma(const MvbSgns* h, void* stream);
+
 extern "C" int mvb_sgns_train(const MvbSgns* h, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (h->n_tokens <= 0) return 0;
@@ -409,11 +412,21 @@ extern "C" int mvb_sgns_train(const MvbSgns* h, void* stream) {
     int64_t blocks = (warps_needed + 3) / 4;
     int64_t cap = (int64_t)sms * 16;
     if (blocks > cap) blocks = cap;
+    int variant = h->variant;
+    if (const char* e = getenv("MVB_SGNS_VARIANT")) variant = atoi(e);
+    if (variant == 10 && h->negative <= 6 && h->window <= 15) return mvb_sgns_train_tma(h, stream);
     switch (vpl) {
-      case 1: sgns_fast_kernel<1, 5><<<(int)blocks, 128, 0, st>>>(d); break;
-      case 2: sgns_fast_kernel<2, 5><<<(int)blocks, 128, 0, st>>>(d); break;
-      case 3: sgns_fast_kernel<3, 5><<<(int)blocks, 128, 0, st>>>(d); break;
-      default: sgns_fast_kernel<4, 3><<<(int)blocks, 128, 0, st>>>(d); break;
+      case 1: sgns_fast_kernel<1, 5, 4><<<(int)blocks, 128, 0, st>>>(d); break;
+      case 2: sgns_fast_kernel<2, 5, 3><<<(int)blocks, 128, 0, st>>>(d); break;
+      case 3:
+        // register/occupancy trade-off: KB rows of 12 registers each stay live per warp
+        // measured on B200 (dim 300, K 5): KB=5 31.5, KB=3 41.4, KB=2 40.4, KB=1 46.4 Mwords/s
+        if (variant == 5) sgns_fast_kernel<3, 5, 3><<<(int)blocks, 128, 0, st>>>(d);
+        else if (variant == 3) sgns_fast_kernel<3, 3, 4><<<(int)blocks, 128, 0, st>>>(d);
+        else if (variant == 2) sgns_fast_kernel<3, 2, 5><<<(int)blocks, 128, 0, st>>>(d);
+        else sgns_fast_kernel<3, 1, 6><<<(int)blocks, 128, 0, st>>>(d);
+        break;
+      default: sgns_fast_kernel<4, 2, 4><<<(int)blocks, 128, 0, st>>>(d); break;
     }
   } else {
     size_t smem = (size_t)4 * 2 * h->dim * sizeof(float);

@@ -1,0 +1,383 @@
+// multiverso-b200 :: K7 (TMA variant) -- skip-gram negative sampling as a bulk-copy pipeline.
+//
+// The register kernel (sgns.cu) is occupancy/latency bound: every warp owns its rows in
+// registers, so only ~12-20 warps fit per SM and each pays the full DRAM latency per sample.
+// This variant moves the row traffic onto the TMA engine:
+//
+//   producer warps  (4 independent pipelines per CTA) one (context -> centre) sample per 8-lane group: lane 0 = input row,
+//                   lane 1 = centre row, lanes 2..7 = negatives (hash RNG -> alias table),
+//                   each lane issues ONE cp.async.bulk (UBLKCP) of its 4*D-byte row into the
+//                   sample's shared-memory stage; completion is counted on the stage's
+//                   mbarrier (expect_tx / complete_tx).  ~24 stages = ~200 KB in flight per SM.
+//   consumer warps  wait on the stage, pull the 2+K rows from shared memory into registers,
+//                   1+K dots with interleaved butterfly reductions, sigmoid / error terms,
+//                   write the rank-1 updates back into the stage in place, then ONE lane issues
+//                   cp.reduce.async.bulk .add.f32 per row: the TMA engine scatter-adds the rows
+//                   into HBM/L2 (atomic accumulate: concurrent samples on the same hot row add
+//                   up instead of overwriting).  The stage is recycled when the bulk-group's
+//                   shared-memory reads have completed (wait_group.read).
+//
+// Same sample schedule as ParseSentence (wordembedding.cpp:216-257): per centre p a random
+// window shrink, contexts stop at sentence breaks, one sample per context word, K negatives
+// per sample drawn from unigram^0.75 (or the block pool), target == centre is skipped.
+#include <cstdlib>
+#include "mvb_common.cuh"
+
+namespace {
+
+constexpr int kMaxRows = 8;        // input + centre + up to 6 negatives
+constexpr int kPipes = 4;          // independent producer->consumer pipelines per CTA
+constexpr int kConsPerPipe = 2;    // consumer warps per pipeline
+constexpr int kConsumers = kPipes * kConsPerPipe;
+constexpr int kMetaBytes = 128;
+
+struct TmaDev {
+  const int* tokens;
+  int64_t n_tokens;
+  float* w_in;
+  float* w_out;
+  int dim;
+  int64_t ld;
+  int window, negative;
+  float lr;
+  const float* alias_prob;
+  const int* alias_idx;
+  int vocab;
+  const int* neg_pool;
+  int neg_pool_size;
+  const int* map_in;
+  const int* map_out;
+  uint64_t seed;
+  float* loss_sum;
+  unsigned long long* pair_count;
+  int stages;
+  int row_bytes;      // 4 * dim
+  int stage_bytes;    // kMetaBytes + rows * row_bytes (16B aligned)
+  int defer_release;  // recycle a slot one sample later (needs >= 2 slots per consumer)
+};
+
+struct StageMeta {
+  float* ptr[kMaxRows];   // global row addresses (nullptr = row not used)
+  int n_rows;             // 0 => sentinel (consumer exits)
+  int pad[15];
+};
+static_assert(sizeof(StageMeta) == kMetaBytes, "meta size");
+
+MVB_DEVINL uint64_t hash64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+MVB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+MVB_DEVINL void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+MVB_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+MVB_DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+MVB_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+MVB_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+MVB_DEVINL void bulk_reduce_add_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+MVB_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+MVB_DEVINL void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+MVB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+MVB_DEVINL float sigm_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+MVB_DEVINL float softplus_neg(float x) { return fmaxf(-x, 0.f) + log1pf(__expf(-fabsf(x))); }
+
+template <int VPL>
+__global__ void __launch_bounds__(32 * (kPipes + kConsumers), 1)
+sgns_tma_kernel(const __grid_constant__ TmaDev a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [full barriers][empty barriers][stage 0][stage 1]...
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + a.stages;
+  unsigned char* stage_base = smem + ((2 * a.stages * 8 + 127) / 128) * 128;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rows_per_sample = 2 + a.negative;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int S = a.stages / kPipes;                 // slots per pipeline
+  if (warp < kPipes) {
+    // ================================ PRODUCERS =========================================
+    // One producer warp per pipeline. Per centre position the warp holds the token window in
+    // registers (lane i = token p-W+i), so sample validity needs no dependent loads; each
+    // 8-lane group then builds one (context -> centre) sample: lane 0 input row, lane 1 centre
+    // row, lanes 2.. negatives (independent hash RNG per lane -> alias table).
+    const int pipe = warp;
+    uint64_t* pfull = full_bar + pipe * S;
+    uint64_t* pempty = empty_bar + pipe * S;
+    unsigned char* pstage = stage_base + (size_t)pipe * S * a.stage_bytes;
+    const int W = a.window;
+    const int grp = lane >> 3, sub = lane & 7;
+    int64_t n_emitted = 0;
+    const int64_t stride = (int64_t)gridDim.x * kPipes;
+    for (int64_t p0 = (int64_t)blockIdx.x * kPipes + pipe; p0 < a.n_tokens; p0 += stride) {
+      const int64_t q = p0 - W + lane;
+      const int tok = (lane <= 2 * W && q >= 0 && q < a.n_tokens) ? __ldg(a.tokens + q) : -1;
+      const int center = __shfl_sync(0xffffffffu, tok, W);
+      if (center < 0) continue;
+      const uint32_t brk = __ballot_sync(0xffffffffu, tok < 0);
+      const uint64_t prng = hash64(a.seed ^ (uint64_t)(p0 + 1) * 0x9E3779B97F4A7C15ull);
+      const int off = (int)((prng >> 16) % (uint64_t)W);
+      for (int base = 0; base < 2 * W; base += 4) {
+        const int ip = base + grp;                        // candidate context slot of this group
+        const int i = ip < W ? ip : ip + 1;               // window index (centre sits at W)
+        bool valid = ip < 2 * W && i >= off && i < 2 * W + 1 - off;
+        const uint32_t between = (i < W) ? (((1u << W) - 1u) & ~((1u << i) - 1u))
+                                         : (((1u << (i + 1)) - 1u) & ~((1u << (W + 1)) - 1u));
+        const int ctx = __shfl_sync(0xffffffffu, tok, i & 31);
+        valid = valid && !(brk & between) && ctx >= 0;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid && sub == 0);
+        if (vmask == 0) continue;
+        const uint32_t before = vmask & ((1u << (grp * 8)) - 1u);
+        const int64_t n = n_emitted + __popc(before);
+        n_emitted += __popc(vmask);
+        const int slot = (int)(n % S);
+        const uint32_t round = (uint32_t)(n / S);
+        unsigned char* st = pstage + (size_t)slot * a.stage_bytes;
+        StageMeta* meta = reinterpret_cast<StageMeta*>(st);
+        unsigned char* rows = st + kMetaBytes;
+        float* gptr = nullptr;
+        if (valid) {
+          if (sub == 0) {
+            int rid = a.map_in ? __ldg(a.map_in + ctx) : ctx;
+            gptr = a.w_in + (int64_t)rid * a.ld;
+          } else if (sub == 1) {
+            int rid = a.map_out ? __ldg(a.map_out + center) : center;
+            gptr = a.w_out + (int64_t)rid * a.ld;
+          } else if (sub < rows_per_sample) {
+            uint64_t r = hash64(prng ^ ((uint64_t)(ip * 8 + sub) * 0xD6E8FEB86659FD93ull));
+            int tgt;
+            if (a.neg_pool) {
+              tgt = __ldg(a.neg_pool + (r >> 8) % (uint64_t)a.neg_pool_size);
+            } else {
+              uint32_t idx = (uint32_t)((r >> 32) % (uint64_t)a.vocab);
+              float u = (float)(r & 0xFFFFFF) * (1.0f / 16777216.0f);
+              float pr = __ldg(a.alias_prob + idx);
+              int al = __ldg(a.alias_idx + idx);
+              tgt = u < pr ? (int)idx : al;
+            }
+            if (tgt != center) {
+              int rid = a.map_out ? __ldg(a.map_out + tgt) : tgt;
+              gptr = a.w_out + (int64_t)rid * a.ld;
+            }
+          }
+          // the consumer must have released this slot (first round passes immediately)
+          mbar_wait(pempty + slot, (round & 1u) ^ 1u);
+          meta->ptr[sub] = gptr;
+        }
+        const uint32_t have_all = __ballot_sync(0xffffffffu, valid && gptr != nullptr);
+        __syncwarp();   // every lane's meta pointer is written before the release-arrive
+        if (valid && sub == 0) {
+          meta->n_rows = rows_per_sample;
+          const uint32_t have = have_all & (0xFFu << (grp * 8));
+          mbar_arrive_expect_tx(pfull + slot, (uint32_t)__popc(have) * (uint32_t)a.row_bytes);
+        }
+        __syncwarp();   // expect_tx is armed before any copy can complete_tx
+        if (valid && gptr)
+          bulk_g2s(rows + (size_t)sub * a.row_bytes, gptr, (uint32_t)a.row_bytes, pfull + slot);
+      }
+    }
+    // sentinels: one per consumer of this pipeline, in ring order
+    for (int c = 0; c < kConsPerPipe; ++c) {
+      const int64_t n = n_emitted + c;
+      const int slot = (int)(n % S);
+      const uint32_t round = (uint32_t)(n / S);
+      if (lane == 0) {
+        mbar_wait(pempty + slot, (round & 1u) ^ 1u);
+        StageMeta* meta = reinterpret_cast<StageMeta*>(pstage + (size_t)slot * a.stage_bytes);
+        meta->n_rows = 0;
+        mbar_arrive(pfull + slot);
+      }
+    }
+  } else {
+    // ================================ CONSUMERS =========================================
+    const int cw = warp - kPipes;
+    const int pipe = cw % kPipes, cidx = cw / kPipes;
+    uint64_t* pfull = full_bar + pipe * S;
+    uint64_t* pempty = empty_bar + pipe * S;
+    unsigned char* pstage = stage_base + (size_t)pipe * S * a.stage_bytes;
+    const int nvec = a.dim >> 2;
+    float loss_acc = 0.f;
+    unsigned long long pairs_acc = 0ull;
+    int prev_slot = -1;
+    for (int64_t n = cidx;; n += kConsPerPipe) {
+      const int slot = (int)(n % S);
+      const uint32_t round = (uint32_t)(n / S);
+      unsigned char* st = pstage + (size_t)slot * a.stage_bytes;
+      StageMeta* meta = reinterpret_cast<StageMeta*>(st);
+      unsigned char* rows = st + kMetaBytes;
+      mbar_wait(pfull + slot, round & 1u);
+      const int n_rows = meta->n_rows;
+      if (n_rows == 0) break;
+      // ---- pull rows into registers ----
+      float4 h[VPL], r[kMaxRows - 1][VPL];
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int c = lane + 32 * j;
+        h[j] = c < nvec ? *reinterpret_cast<const float4*>(rows + (size_t)c * 16) : make_float4(0, 0, 0, 0);
+      }
+      float f[kMaxRows - 1];
+      bool used[kMaxRows - 1];
+#pragma unroll
+      for (int k = 0; k < kMaxRows - 1; ++k) {
+        used[k] = (k + 1 < n_rows) && meta->ptr[k + 1] != nullptr;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int c = lane + 32 * j;
+          r[k][j] = (used[k] && c < nvec)
+                        ? *reinterpret_cast<const float4*>(rows + (size_t)(k + 1) * a.row_bytes + (size_t)c * 16)
+                        : make_float4(0, 0, 0, 0);
+          s = fmaf(h[j].x, r[k][j].x, s); s = fmaf(h[j].y, r[k][j].y, s);
+          s = fmaf(h[j].z, r[k][j].z, s); s = fmaf(h[j].w, r[k][j].w, s);
+        }
+        f[k] = s;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < kMaxRows - 1; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], o);
+      }
+      // ---- errors, hidden error, in-place deltas ----
+      float4 herr[VPL];
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) herr[j] = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < kMaxRows - 1; ++k) {
+        if (!used[k]) continue;
+        const float label = (k == 0) ? 1.f : 0.f;
+        const float g = (label - sigm_fast(f[k])) * a.lr;
+        if (a.loss_sum) loss_acc += softplus_neg(k == 0 ? f[k] : -f[k]);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int c = lane + 32 * j;
+          herr[j].x = fmaf(g, r[k][j].x, herr[j].x); herr[j].y = fmaf(g, r[k][j].y, herr[j].y);
+          herr[j].z = fmaf(g, r[k][j].z, herr[j].z); herr[j].w = fmaf(g, r[k][j].w, herr[j].w);
+          if (c < nvec)
+            *reinterpret_cast<float4*>(rows + (size_t)(k + 1) * a.row_bytes + (size_t)c * 16) =
+                make_float4(g * h[j].x, g * h[j].y, g * h[j].z, g * h[j].w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nvec) *reinterpret_cast<float4*>(rows + (size_t)c * 16) = herr[j];
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        // TMA scatter-add of the sample's rows; recycle the PREVIOUS slot once its reads are done
+        for (int k = 0; k < n_rows; ++k)
+          if (meta->ptr[k]) bulk_reduce_add_s2g(meta->ptr[k], rows + (size_t)k * a.row_bytes, (uint32_t)a.row_bytes);
+        bulk_commit();
+        if (a.defer_release) {
+          if (prev_slot >= 0) {
+            bulk_wait_read<1>();
+            mbar_arrive(pempty + prev_slot);
+          }
+        } else {
+          bulk_wait_read<0>();
+          mbar_arrive(pempty + slot);
+        }
+      }
+      prev_slot = a.defer_release ? slot : -1;
+      ++pairs_acc;
+      __syncwarp();
+    }
+    if (lane == 0) {
+      bulk_wait_read<0>();
+      if (prev_slot >= 0) mbar_arrive(pempty + prev_slot);
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes globally performed
+      if (a.loss_sum && loss_acc != 0.f) atomicAdd(a.loss_sum, loss_acc);
+      if (a.pair_count && pairs_acc) atomicAdd(a.pair_count, pairs_acc);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int mvb_sgns_train_tma(const MvbSgns* h, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->n_tokens <= 0) return 0;
+  if (h->cbow || h->hs || h->use_adagrad || h->negative < 1 || h->negative > kMaxRows - 2) return -20;
+  if (h->dim % 4 || h->ld % 4 || h->dim > 512 || h->window < 1 || h->window > 15) return -21;
+  TmaDev a{};
+  a.tokens = h->tokens; a.n_tokens = h->n_tokens; a.w_in = h->w_in; a.w_out = h->w_out;
+  a.dim = h->dim; a.ld = h->ld; a.window = h->window; a.negative = h->negative; a.lr = h->lr;
+  a.alias_prob = h->alias_prob; a.alias_idx = h->alias_idx; a.vocab = h->vocab;
+  a.neg_pool = h->neg_pool; a.neg_pool_size = h->neg_pool_size; a.map_in = h->map_in;
+  a.map_out = h->map_out; a.seed = h->seed; a.loss_sum = h->loss_sum; a.pair_count = h->pair_count;
+  a.row_bytes = h->dim * 4;
+  a.stage_bytes = ((kMetaBytes + (2 + h->negative) * a.row_bytes + 127) / 128) * 128;
+  int dev = 0, max_smem = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int budget = max_smem - 2048;
+  int stages = budget / a.stage_bytes;
+  stages = stages / kConsumers * kConsumers;     // static slot -> consumer mapping per pipeline
+  if (stages > 64) stages = 64;
+  if (stages < kConsumers) return -22;
+  if (const char* e = getenv("MVB_SGNS_STAGES")) {
+    int s = atoi(e) / kConsumers * kConsumers;
+    if (s >= kConsumers && s <= stages) stages = s;
+  }
+  a.stages = stages;
+  a.defer_release = stages >= 2 * kConsumers ? 1 : 0;   // >= 2 slots per consumer
+  size_t smem = ((2 * stages * 8 + 127) / 128) * 128 + (size_t)stages * a.stage_bytes;
+  const int vpl = (h->dim / 4 + 31) / 32;
+  const int threads = 32 * (kPipes + kConsumers);
+  int blocks = mvb_num_sms();
+  if ((int64_t)blocks > h->n_tokens) blocks = (int)h->n_tokens;
+#define MVB_LAUNCH_TMA(V)                                                                       \
+  do {                                                                                          \
+    MVB_CUDA_CHECK(cudaFuncSetAttribute(sgns_tma_kernel<V>,                                     \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sgns_tma_kernel<V><<<blocks, threads, smem, st>>>(a);                                       \
+  } while (0)
+  switch (vpl) {
+    case 1: MVB_LAUNCH_TMA(1); break;
+    case 2: MVB_LAUNCH_TMA(2); break;
+    case 3: MVB_LAUNCH_TMA(3); break;
+    default: MVB_LAUNCH_TMA(4); break;
+  }
+#undef MVB_LAUNCH_TMA
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

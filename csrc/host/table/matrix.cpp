@@ -1,0 +1,147 @@
+// Matrix<T> with sparse delta-pull and optional wire compression
+// (see include/multiverso/table/matrix.h and table/sparse_matrix_table.h).
+#include "multiverso/table/matrix.h"
+#include "multiverso/multiverso.h"
+#include "multiverso/table/sparse_matrix_table.h"
+#include "multiverso/util/log.h"
+#include "multiverso/util/quantization_util.h"
+
+namespace multiverso {
+
+namespace {
+const integer_t kWholeTable = -1;
+inline bool IsWhole(const Blob& keys) { return keys.size<integer_t>() == 1 && keys.As<integer_t>(0) == kWholeTable; }
+}  // namespace
+
+// ======================================= worker =========================================
+template <typename T>
+MatrixWorker<T>::MatrixWorker(integer_t num_row, integer_t num_col, bool is_sparse, bool compress)
+    : MatrixWorkerTable<T>(num_row, num_col), is_sparse_(is_sparse), compress_(compress) {}
+
+// Whole-table Add on a sparse table: ship only the rows that are not all-zero
+// (src/table/matrix.cpp:146-182).
+template <typename T>
+int MatrixWorker<T>::SubmitWholeAdd(T* data, size_t size, const AddOption* opt) {
+  if (!is_sparse_) return MatrixWorkerTable<T>::SubmitWholeAdd(data, size, opt);
+  const integer_t R = this->num_row_, C = this->num_col_;
+  std::vector<integer_t> rows;
+  for (integer_t r = 0; r < R; ++r) {
+    const T* row = data + r * C;
+    bool nz = false;
+    for (integer_t c = 0; c < C && !nz; ++c) nz = row[c] != T(0);
+    if (nz) rows.push_back(r);
+  }
+  if (rows.empty()) {
+    // nothing to ship: an already-complete request (the reference sends a dummy zero row)
+    const int id = this->NewRequest();
+    this->Reset(id, 0);
+    return id;
+  }
+  Blob vals(rows.size() * C * sizeof(T));
+  for (size_t i = 0; i < rows.size(); ++i)
+    std::memcpy(vals.data() + i * C * sizeof(T), data + rows[i] * C, C * sizeof(T));
+  return WorkerTable::AddAsync(Blob(rows.data(), rows.size() * sizeof(integer_t)), std::move(vals), opt);
+}
+
+template <typename T>
+void MatrixWorker<T>::FilterOutgoing(std::vector<Blob>* blobs) {
+  if (!compress_) return;
+  // SparseFilter(clip = 0, skip_option_blob): (index,value) pairs when < half is non-zero
+  const bool has_opt = blobs->size() == 3;
+  SparseFilter<T, int32_t> filter(0.0, has_opt);
+  std::vector<Blob> out;
+  filter.FilterIn(*blobs, &out);
+  *blobs = std::move(out);
+}
+
+// ======================================= server =========================================
+template <typename T>
+MatrixServer<T>::MatrixServer(integer_t num_row, integer_t num_col, bool is_sparse, bool is_pipeline,
+                              bool compress)
+    : MatrixServerTable<T>(num_row, num_col), is_sparse_(is_sparse), compress_(compress) {
+  slots_ = MV_NumWorkers() * (is_pipeline ? 2 : 1);
+  if (is_sparse_)
+    stale_.assign(static_cast<size_t>(slots_), std::vector<unsigned char>(static_cast<size_t>(this->my_num_row_), 1));
+}
+
+template <typename T>
+void MatrixServer<T>::MarkStale(const integer_t* rows, size_t n, bool all) {
+  for (auto& per : stale_) {
+    if (all) std::fill(per.begin(), per.end(), 1);
+    else for (size_t i = 0; i < n; ++i) per[static_cast<size_t>(rows[i] - this->row_offset_)] = 1;
+  }
+}
+
+template <typename T>
+void MatrixServer<T>::ProcessAdd(const std::vector<Blob>& data) {
+  std::vector<Blob> plain;
+  const std::vector<Blob>* in = &data;
+  if (compress_) {
+    SparseFilter<T, int32_t> filter(0.0, true);
+    filter.FilterOut(data, &plain);
+    in = &plain;
+  }
+  MatrixServerTable<T>::ProcessAdd(*in);
+  if (is_sparse_) {
+    const Blob& keys = (*in)[0];
+    if (IsWhole(keys)) MarkStale(nullptr, 0, true);
+    else MarkStale(&keys.As<integer_t>(0), keys.size<integer_t>(), false);
+  }
+}
+
+template <typename T>
+void MatrixServer<T>::ProcessGet(const std::vector<Blob>& data, std::vector<Blob>* result) {
+  if (!is_sparse_) {
+    MatrixServerTable<T>::ProcessGet(data, result);
+    return;
+  }
+  const Blob& keys = data[0];
+  int worker = -1;
+  if (data.size() >= 2 && data[1].size() >= sizeof(int)) worker = GetOption(data[1].data(), data[1].size()).worker_id();
+  if (!IsWhole(keys)) {
+    // explicit rows are always served; they become up to date for that worker
+    MatrixServerTable<T>::ProcessGet(data, result);
+    if (worker >= 0 && worker < slots_)
+      for (size_t i = 0; i < keys.size<integer_t>(); ++i)
+        stale_[worker][static_cast<size_t>(keys.As<integer_t>(i) - this->row_offset_)] = 0;
+    return;
+  }
+  if (worker < 0 || worker >= slots_) {   // worker_id == -1: return everything
+    MatrixServerTable<T>::ProcessGet(data, result);
+    return;
+  }
+  std::vector<integer_t> rows;
+  auto& mine = stale_[worker];
+  for (integer_t r = 0; r < this->my_num_row_; ++r)
+    if (mine[static_cast<size_t>(r)]) {
+      rows.push_back(r + this->row_offset_);
+      mine[static_cast<size_t>(r)] = 0;
+    }
+  const size_t C = static_cast<size_t>(this->num_col_);
+  Blob ids(rows.size() * sizeof(integer_t));
+  Blob vals(rows.size() * C * sizeof(T));
+  for (size_t i = 0; i < rows.size(); ++i) {
+    ids.As<integer_t>(i) = rows[i];
+    std::memcpy(vals.data() + i * C * sizeof(T),
+                this->storage_.data() + static_cast<size_t>(rows[i] - this->row_offset_) * C, C * sizeof(T));
+  }
+  // an explicit (possibly empty) row list -- no row-0 placeholder
+  result->push_back(std::move(ids));
+  result->push_back(std::move(vals));
+  result->emplace_back(&this->server_id_, sizeof(int));
+}
+
+template class MatrixWorker<float>;
+template class MatrixWorker<double>;
+template class MatrixWorker<int>;
+template class MatrixServer<float>;
+template class MatrixServer<double>;
+template class MatrixServer<int>;
+template class SparseMatrixWorkerTable<float>;
+template class SparseMatrixWorkerTable<double>;
+template class SparseMatrixWorkerTable<int>;
+template class SparseMatrixServerTable<float>;
+template class SparseMatrixServerTable<double>;
+template class SparseMatrixServerTable<int>;
+
+}  // namespace multiverso

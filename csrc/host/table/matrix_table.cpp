@@ -1,0 +1,312 @@
+// MatrixTable<T> (see include/multiverso/table/matrix_table.h).
+#include "multiverso/table/matrix_table.h"
+#include <algorithm>
+#include <random>
+#include "multiverso/multiverso.h"
+#include "multiverso/util/log.h"
+
+namespace multiverso {
+
+namespace {
+const integer_t kWholeTable = -1;
+inline bool IsWhole(const Blob& keys) { return keys.size<integer_t>() == 1 && keys.As<integer_t>(0) == kWholeTable; }
+}  // namespace
+
+RowPartition::RowPartition(integer_t rows, int servers) : num_row(rows) {
+  if (rows >= servers) {
+    num_servers = servers;
+    rows_each = rows / servers;
+  } else {
+    num_servers = static_cast<int>(std::max<integer_t>(rows, 1));   // one row per server
+    rows_each = 1;
+  }
+  // servers beyond the actual count own nothing; the last actual server takes the remainder
+  row_begin.assign(static_cast<size_t>(servers) + 1, rows);
+  for (int s = 0; s < num_servers; ++s) row_begin[s] = rows_each * s;
+}
+
+int RowPartition::ServerOf(integer_t row) const {
+  integer_t s = row / rows_each;
+  if (s >= num_servers) s = num_servers - 1;
+  return static_cast<int>(s);
+}
+
+// ======================================= worker =========================================
+template <typename T>
+MatrixWorkerTable<T>::MatrixWorkerTable(integer_t num_row, integer_t num_col)
+    : num_row_(num_row), num_col_(num_col), part_(num_row, MV_NumServers()) {
+  CHECK(num_row > 0 && num_col > 0);
+  Log::Debug("worker %d created MatrixTable %lld x %lld", MV_WorkerId(), (long long)num_row, (long long)num_col);
+}
+
+template <typename T>
+int MatrixWorkerTable<T>::SubmitGet(GetRecord&& rec, Blob keys, const GetOption* opt) {
+  const int id = NewRequest();
+  {
+    std::lock_guard<std::mutex> lk(rec_mu_);
+    records_[id] = std::move(rec);
+  }
+  MessagePtr msg(new Message());
+  msg->set_src(MV_Rank());
+  msg->set_type(MsgType::Request_Get);
+  msg->set_msg_id(id);
+  msg->set_table_id(table_id_);
+  msg->Push(std::move(keys));
+  if (opt) msg->Push(Blob(opt->data(), opt->size()));
+  Zoo::Get()->SendTo("worker", msg);
+  return id;
+}
+
+template <typename T>
+int MatrixWorkerTable<T>::GetAsync(T* data, size_t size, const GetOption* opt) {
+  CHECK(size == static_cast<size_t>(num_row_ * num_col_));
+  GetRecord rec;
+  rec.whole = data;
+  return SubmitGet(std::move(rec), Blob(&kWholeTable, sizeof(integer_t)), opt);
+}
+template <typename T>
+int MatrixWorkerTable<T>::GetAsync(integer_t row_id, T* data, size_t size, const GetOption* opt) {
+  CHECK(size == static_cast<size_t>(num_col_) && row_id >= 0 && row_id < num_row_);
+  GetRecord rec;
+  rec.rows[row_id] = data;
+  return SubmitGet(std::move(rec), Blob(&row_id, sizeof(integer_t)), opt);
+}
+template <typename T>
+int MatrixWorkerTable<T>::GetAsync(const std::vector<integer_t>& row_ids, const std::vector<T*>& data_vec,
+                                   size_t size, const GetOption* opt) {
+  CHECK(size == static_cast<size_t>(num_col_) && row_ids.size() == data_vec.size());
+  GetRecord rec;
+  for (size_t i = 0; i < row_ids.size(); ++i) rec.rows[row_ids[i]] = data_vec[i];
+  return SubmitGet(std::move(rec), Blob(row_ids.data(), row_ids.size() * sizeof(integer_t)), opt);
+}
+template <typename T>
+int MatrixWorkerTable<T>::GetAsync(T* data, size_t size, integer_t* row_ids, int n, const GetOption* opt) {
+  CHECK(size == static_cast<size_t>(n) * num_col_);
+  GetRecord rec;
+  for (int i = 0; i < n; ++i) rec.rows[row_ids[i]] = data + static_cast<size_t>(i) * num_col_;
+  return SubmitGet(std::move(rec), Blob(row_ids, sizeof(integer_t) * n), opt);
+}
+
+template <typename T> void MatrixWorkerTable<T>::Get(T* d, size_t s, const GetOption* o) { Wait(GetAsync(d, s, o)); }
+template <typename T> void MatrixWorkerTable<T>::Get(integer_t r, T* d, size_t s, const GetOption* o) { Wait(GetAsync(r, d, s, o)); }
+template <typename T> void MatrixWorkerTable<T>::Get(const std::vector<integer_t>& r, const std::vector<T*>& d, size_t s, const GetOption* o) { Wait(GetAsync(r, d, s, o)); }
+template <typename T> void MatrixWorkerTable<T>::Get(T* d, size_t s, integer_t* r, int n, const GetOption* o) { Wait(GetAsync(d, s, r, n, o)); }
+
+template <typename T>
+int MatrixWorkerTable<T>::SubmitWholeAdd(T* data, size_t size, const AddOption* opt) {
+  return WorkerTable::AddAsync(Blob(&kWholeTable, sizeof(integer_t)), Blob(data, size * sizeof(T)), opt);
+}
+
+template <typename T>
+int MatrixWorkerTable<T>::AddAsync(T* data, size_t size, const AddOption* opt) {
+  CHECK(size == static_cast<size_t>(num_row_ * num_col_));
+  return SubmitWholeAdd(data, size, opt);
+}
+template <typename T>
+int MatrixWorkerTable<T>::AddAsync(integer_t row_id, T* data, size_t size, const AddOption* opt) {
+  CHECK(size == static_cast<size_t>(num_col_) && row_id >= 0 && row_id < num_row_);
+  return WorkerTable::AddAsync(Blob(&row_id, sizeof(integer_t)), Blob(data, size * sizeof(T)), opt);
+}
+template <typename T>
+int MatrixWorkerTable<T>::AddAsync(const std::vector<integer_t>& row_ids, const std::vector<T*>& data_vec,
+                                   size_t size, const AddOption* opt) {
+  CHECK(size == static_cast<size_t>(num_col_) && row_ids.size() == data_vec.size());
+  Blob vals(row_ids.size() * num_col_ * sizeof(T));
+  for (size_t i = 0; i < row_ids.size(); ++i)
+    std::memcpy(vals.data() + i * num_col_ * sizeof(T), data_vec[i], num_col_ * sizeof(T));
+  return WorkerTable::AddAsync(Blob(row_ids.data(), row_ids.size() * sizeof(integer_t)), std::move(vals), opt);
+}
+template <typename T>
+int MatrixWorkerTable<T>::AddAsync(T* data, size_t size, integer_t* row_ids, int n, const AddOption* opt) {
+  CHECK(size == static_cast<size_t>(n) * num_col_);
+  return WorkerTable::AddAsync(Blob(row_ids, sizeof(integer_t) * n), Blob(data, size * sizeof(T)), opt);
+}
+
+template <typename T> void MatrixWorkerTable<T>::Add(T* d, size_t s, const AddOption* o) { Wait(AddAsync(d, s, o)); }
+template <typename T> void MatrixWorkerTable<T>::Add(integer_t r, T* d, size_t s, const AddOption* o) { Wait(AddAsync(r, d, s, o)); }
+template <typename T> void MatrixWorkerTable<T>::Add(const std::vector<integer_t>& r, const std::vector<T*>& d, size_t s, const AddOption* o) { Wait(AddAsync(r, d, s, o)); }
+template <typename T> void MatrixWorkerTable<T>::Add(T* d, size_t s, integer_t* r, int n, const AddOption* o) { Wait(AddAsync(d, s, r, n, o)); }
+
+template <typename T>
+int MatrixWorkerTable<T>::Partition(const std::vector<Blob>& kv, MsgType type,
+                                    std::unordered_map<int, std::vector<Blob>>* out) {
+  const bool is_add = type == MsgType::Request_Add;
+  CHECK(kv.size() >= (is_add ? 2u : 1u));
+  const Blob* option = (kv.size() > (is_add ? 2u : 1u)) ? &kv.back() : nullptr;
+  const Blob& keys = kv[0];
+  const size_t row_bytes = static_cast<size_t>(num_col_) * sizeof(T);
+  if (IsWhole(keys)) {
+    for (int s = 0; s < part_.num_servers; ++s) {
+      const integer_t lo = part_.row_begin[s], hi = part_.row_begin[s + 1];
+      if (hi == lo) continue;
+      std::vector<Blob>& v = (*out)[s];
+      v.push_back(keys);
+      if (is_add) v.emplace_back(kv[1].data() + lo * row_bytes, static_cast<size_t>(hi - lo) * row_bytes);
+      if (option) v.push_back(*option);
+    }
+  } else {
+    const size_t n = keys.size<integer_t>();
+    std::unordered_map<int, std::vector<size_t>> bucket;
+    for (size_t i = 0; i < n; ++i) {
+      const integer_t r = keys.As<integer_t>(i);
+      CHECK(r >= 0 && r < num_row_);
+      bucket[part_.ServerOf(r)].push_back(i);
+    }
+    for (auto& b : bucket) {
+      Blob ids(b.second.size() * sizeof(integer_t));
+      for (size_t j = 0; j < b.second.size(); ++j) ids.As<integer_t>(j) = keys.As<integer_t>(b.second[j]);
+      std::vector<Blob>& v = (*out)[b.first];
+      v.push_back(std::move(ids));
+      if (is_add) {
+        Blob vals(b.second.size() * row_bytes);
+        for (size_t j = 0; j < b.second.size(); ++j)
+          std::memcpy(vals.data() + j * row_bytes, kv[1].data() + b.second[j] * row_bytes, row_bytes);
+        v.push_back(std::move(vals));
+      }
+      if (option) v.push_back(*option);
+    }
+  }
+  if (is_add)
+    for (auto& kvp : *out) FilterOutgoing(&kvp.second);
+  return static_cast<int>(out->size());
+}
+
+template <typename T>
+void MatrixWorkerTable<T>::ProcessReplyGet(std::vector<Blob>& reply, int msg_id) {
+  CHECK(reply.size() == 3);
+  const Blob& keys = reply[0];
+  const int sid = reply[2].As<int>(0);
+  const size_t row_bytes = static_cast<size_t>(num_col_) * sizeof(T);
+  std::lock_guard<std::mutex> lk(rec_mu_);
+  GetRecord& rec = records_.at(msg_id);
+  if (IsWhole(keys)) {
+    CHECK(rec.whole != nullptr);
+    std::memcpy(rec.whole + part_.row_begin[sid] * num_col_, reply[1].data(), reply[1].size());
+    return;
+  }
+  const size_t n = keys.size<integer_t>();
+  CHECK(reply[1].size() == n * row_bytes);
+  for (size_t i = 0; i < n; ++i) {
+    const integer_t r = keys.As<integer_t>(i);
+    T* dst = nullptr;
+    auto it = rec.rows.find(r);
+    if (it != rec.rows.end()) dst = it->second;
+    else if (rec.whole) dst = rec.whole + r * num_col_;   // sparse delta-pull into the whole buffer
+    if (dst) std::memcpy(dst, reply[1].data() + i * row_bytes, row_bytes);
+  }
+}
+
+template <typename T>
+void MatrixWorkerTable<T>::OnRequestDone(int msg_id) {
+  std::lock_guard<std::mutex> lk(rec_mu_);
+  records_.erase(msg_id);
+}
+
+// ======================================= server =========================================
+template <typename T>
+void MatrixServerTable<T>::Init(integer_t num_row, integer_t num_col) {
+  server_id_ = MV_ServerId();
+  num_col_ = num_col;
+  RowPartition part(num_row, MV_NumServers());
+  row_offset_ = part.row_begin[server_id_];
+  my_num_row_ = part.row_begin[server_id_ + 1] - row_offset_;
+  storage_.assign(static_cast<size_t>(my_num_row_ * num_col_), T(0));
+  updater_ = Updater<T>::GetUpdater(storage_.size());
+  Log::Debug("server %d created MatrixTable shard: rows [%lld, %lld) x %lld", server_id_,
+             (long long)row_offset_, (long long)(row_offset_ + my_num_row_), (long long)num_col);
+}
+
+template <typename T>
+MatrixServerTable<T>::MatrixServerTable(integer_t num_row, integer_t num_col) { Init(num_row, num_col); }
+
+template <typename T>
+MatrixServerTable<T>::MatrixServerTable(integer_t num_row, integer_t num_col, T lo, T hi) {
+  Init(num_row, num_col);
+  // server-side random-uniform init (matrix_table.cpp:371-384), used by WordEmbedding
+  std::mt19937_64 gen(0x9E3779B97F4A7C15ull + static_cast<uint64_t>(server_id_));
+  std::uniform_real_distribution<double> dist(static_cast<double>(lo), static_cast<double>(hi));
+  for (auto& v : storage_) v = static_cast<T>(dist(gen));
+}
+
+template <typename T>
+MatrixServerTable<T>::MatrixServerTable(const MatrixTableOption<T>& o) {
+  Init(o.num_row, o.num_col);
+  if (o.random_init) {
+    std::mt19937_64 gen(0x9E3779B97F4A7C15ull + static_cast<uint64_t>(server_id_));
+    std::uniform_real_distribution<double> dist(static_cast<double>(o.min_value), static_cast<double>(o.max_value));
+    for (auto& v : storage_) v = static_cast<T>(dist(gen));
+  }
+}
+
+template <typename T>
+MatrixServerTable<T>::~MatrixServerTable() { delete updater_; }
+
+template <typename T>
+void MatrixServerTable<T>::ProcessAdd(const std::vector<Blob>& data) {
+  CHECK(data.size() >= 2);
+  AddOption opt = AddOptionFrom(data, 2);
+  const Blob& keys = data[0];
+  T* vals = reinterpret_cast<T*>(data[1].data());
+  if (IsWhole(keys)) {
+    CHECK(data[1].size() == storage_.size() * sizeof(T));
+    updater_->Update(storage_.size(), storage_.data(), vals, &opt, 0);
+    return;
+  }
+  const size_t n = keys.size<integer_t>();
+  CHECK(data[1].size() == n * num_col_ * sizeof(T));
+  for (size_t i = 0; i < n; ++i) {
+    const integer_t local = keys.As<integer_t>(i) - row_offset_;
+    CHECK(local >= 0 && local < my_num_row_);
+    updater_->Update(static_cast<size_t>(num_col_), storage_.data(), vals + i * num_col_, &opt,
+                     static_cast<size_t>(local * num_col_));
+  }
+}
+
+template <typename T>
+void MatrixServerTable<T>::ProcessGet(const std::vector<Blob>& data, std::vector<Blob>* result) {
+  CHECK(!data.empty());
+  const Blob& keys = data[0];
+  result->push_back(keys);
+  if (IsWhole(keys)) {
+    Blob values(storage_.size() * sizeof(T));
+    updater_->Access(storage_.size(), storage_.data(), reinterpret_cast<T*>(values.data()), 0, nullptr);
+    result->push_back(std::move(values));
+  } else {
+    const size_t n = keys.size<integer_t>();
+    Blob values(n * num_col_ * sizeof(T));
+    for (size_t i = 0; i < n; ++i) {
+      const integer_t local = keys.As<integer_t>(i) - row_offset_;
+      CHECK(local >= 0 && local < my_num_row_);
+      updater_->Access(static_cast<size_t>(num_col_), storage_.data(),
+                       reinterpret_cast<T*>(values.data()) + i * num_col_,
+                       static_cast<size_t>(local * num_col_), nullptr);
+    }
+    result->push_back(std::move(values));
+  }
+  result->emplace_back(&server_id_, sizeof(int));
+}
+
+template <typename T>
+void MatrixServerTable<T>::Store(Stream* s) {
+  s->Write(storage_.data(), storage_.size() * sizeof(T));
+  std::vector<char> st(updater_->StateBytes());
+  if (!st.empty()) {
+    updater_->StoreState(st.data());
+    s->Write(st.data(), st.size());
+  }
+}
+template <typename T>
+void MatrixServerTable<T>::Load(Stream* s) {
+  s->Read(storage_.data(), storage_.size() * sizeof(T));
+  std::vector<char> st(updater_->StateBytes());
+  if (!st.empty() && s->Read(st.data(), st.size()) == st.size()) updater_->LoadState(st.data());
+}
+
+template class MatrixWorkerTable<float>;
+template class MatrixWorkerTable<double>;
+template class MatrixWorkerTable<int>;
+template class MatrixServerTable<float>;
+template class MatrixServerTable<double>;
+template class MatrixServerTable<int>;
+
+}  // namespace multiverso

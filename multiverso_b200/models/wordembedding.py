@@ -155,6 +155,7 @@ class WordEmbedding:
         self._step = 0
         self._map_in = self._map_out = None
         self.kernel_launches = 0
+        self.kernel_variant = 0     # 0 auto | 1,2,3,5 register kernel (negatives in flight) | 10 TMA pipeline
 
     # ------------------------------------------------------------------ lr schedule
     def update_learning_rate(self) -> float:
@@ -190,6 +191,7 @@ class WordEmbedding:
         a.seed = ((0x5DEECE66D * (self.rt.rank + 1)) ^ (self._step * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
         a.loss_sum = self.loss.data_ptr() if compute_loss else None
         a.pair_count = self.pairs.data_ptr()
+        a.variant = self.kernel_variant
         N.check(N.cuda_lib().mvb_sgns_train(C.byref(a), C.c_void_p(N.stream_ptr())), "mvb_sgns_train")
         self.kernel_launches += 1
 

@@ -191,9 +191,7 @@ class Runtime:
         if not self.started:
             return
         import torch
-        for t in list(self.tables):
-            if hasattr(t, "finish_train"):
-                t.finish_train()
+        self._finish_train()
         self.barrier()
         for t in list(self.tables):
             if hasattr(t, "free"):
@@ -216,6 +214,39 @@ class Runtime:
         self._epochs = {}
         self._next_channel = 4
         Runtime._inst = None
+
+    def _finish_train(self) -> None:
+        """Zoo::FinishTrain (src/zoo.cpp:152-161) for the BSP device tables. A rank that is
+        done must (1) stop gating the others -- FIN on every table's ready channel -- and
+        (2) keep serving as an owner: it polls the ready slots of all its tables and runs the
+        fused Add for any epoch every still-active worker has published, until all workers
+        of all tables have finished. Polling (never a blocking wait) keeps multi-table
+        shutdown deadlock-free when ranks finish at different times."""
+        import time
+        import torch
+        bsp = [t for t in self.tables if getattr(t, "needs_drain", lambda: False)()]
+        if not bsp or self.size == 1:
+            return
+        lib = N.cuda_lib()
+        for t in bsp:
+            t.publish_finish()
+        torch.cuda.current_stream().synchronize()
+        pending = list(bsp)
+        deadline = time.time() + 4 * float(FLAGS.get("barrier_timeout_s"))
+        while pending and time.time() < deadline:
+            pads = self.pads.tensor(torch.int64).cpu()
+            progressed = False
+            for t in list(pending):
+                st = t.drain_step(pads)
+                if st == "done":
+                    pending.remove(t)
+                    progressed = True
+                elif st == "served":
+                    progressed = True
+            if not progressed:
+                time.sleep(0.0005)
+        if pending:
+            Log.error("FinishTrain: %d table(s) still waiting for peers at shutdown", len(pending))
 
     # ------------------------------------------------------------------ identity
     def num_workers(self) -> int:

@@ -272,31 +272,38 @@ class DenseDeviceTable(_AsyncOps):
         return self._record(), out
 
     # ------------------------------------------------------------------ BSP shutdown
+    def needs_drain(self) -> bool:
+        return self.sync and self.rt.size > 1 and bool(self._stage) and not self._finished
+
     def finish_train(self) -> None:
-        """Server_Finish_Train: stop gating the BSP epochs on this worker and keep serving
-        the other workers' Adds until every worker has finished (src/zoo.cpp:152-161,
-        src/server.cpp:190-213)."""
-        rt = self.rt
-        if rt.size == 1 or not self.sync or self._finished or not self._stage:
-            self._finished = True
-            return
-        lib = N.cuda_lib()
+        self.rt._finish_train()
+
+    def publish_finish(self) -> None:
+        """Server_Finish_Train: leave EPOCH_FIN in this worker's ready slot on every rank so
+        it never gates a BSP epoch again (src/server.cpp:190-213)."""
+        rt, lib = self.rt, N.cuda_lib()
         self._finished = True
         if rt.is_worker():
             N.check(lib.mvb_signal(rt.pads_array(), rt.rank, rt.size, self.ch_ready,
                                    C.c_uint64(N.EPOCH_FIN), C.c_void_p(N.stream_ptr())), "mvb_signal")
-        buf = self._stage[0]
-        ptrs = [buf.ptrs[rt.worker_id_to_rank(w)] for w in range(self.W)]
-        while True:
-            self._fin.zero_()
-            # staging parity must match what the still-running workers use for this epoch
-            buf = self._stage[self.add_epoch % 2]
+
+    def drain_step(self, pads_host) -> str:
+        """One polling step of the owner-side drain: 'done' when every worker finished,
+        'served' after applying one more epoch for the still-active workers, else 'wait'."""
+        rt = self.rt
+        flags = [int(pads_host[self.ch_ready * N.MAX_RANKS + rt.worker_id_to_rank(w)])
+                 for w in range(self.W)]
+        if all(f >= N.EPOCH_FIN for f in flags):
+            return "done"
+        nxt = self.add_epoch + 1
+        if all(f >= nxt for f in flags):
+            buf = self._stage[self.add_epoch % 2]   # staging parity of epoch nxt
             ptrs = [buf.ptrs[rt.worker_id_to_rank(w)] for w in range(self.W)]
             self._launch_fused(ptrs, [AddOption(0)] * self.W, pads=True, serve_only=True)
             torch.cuda.current_stream().synchronize()
             rt.check_watchdog()
-            if int(self._fin.item()):
-                break
+            return "served"
+        return "wait"
 
     def free(self) -> None:
         for b in [self.shard_buf] + list(self._stage):

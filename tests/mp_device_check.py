@@ -125,8 +125,8 @@ def scenario_async():
         check(f"aggregate_f32_{n_el}", torch.equal(y, torch.full((n_el,), W * (W + 1) / 2.0, device="cuda")))
     # distributed WordEmbedding block (block mode)
     from multiverso_b200.models.wordembedding import WordEmbedding, WordEmbeddingOption, synthetic_zipf_corpus
-    we = WordEmbedding(WordEmbeddingOption(embeding_size=300, init_learning_rate=0.05), 50000)
-    toks = torch.from_numpy(synthetic_zipf_corpus(200000, 50000, 1000, seed=r)).cuda()
+    we = WordEmbedding(WordEmbeddingOption(embeding_size=300, init_learning_rate=0.01), 200000)
+    toks = torch.from_numpy(synthetic_zipf_corpus(400000, 200000, 1000, seed=r)).cuda()
     losses = []
     for it in range(4):
         we.loss.zero_(); we.pairs.zero_()

@@ -138,7 +138,7 @@ def test_kv_table(mv_device):
     assert kv.get(0) == 3.0
     kv.add(0, -4.0)
     assert kv.get(0) == -1.0
-    keys = torch.arange(-500, 500, device="cuda") * 7919
+    keys = torch.arange(-500, 500, device="cuda") * 7919 + 1
     kv.add(keys, torch.ones(1000, device="cuda"))
     kv.add(keys, torch.ones(1000, device="cuda"))
     assert torch.equal(kv.get(keys), torch.full((1000,), 2.0, device="cuda"))

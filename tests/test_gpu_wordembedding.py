@@ -11,14 +11,17 @@ def _sig(x):
     return 1.0 / (1.0 + torch.exp(-x))
 
 
-def test_sgns_fast_kernel_matches_reference(mv_device):
+@pytest.mark.parametrize("variant", [5, 1, 10])
+def test_sgns_fast_kernel_matches_reference(mv_device, variant):
     """window=1 (no random shrink) and a one-word negative pool make the sample schedule
     deterministic: centre p trains (ctx p-1 -> p) then (ctx p+1 -> p), each with K draws of
     the pool word evaluated on pre-update rows. All words distinct, so cross-warp coupling
-    is only through red.add accumulation (order-independent up to O(lr^2))."""
+    is only through red.add accumulation: warps may or may not observe each other's updates
+    (Hogwild), an O(lr^2) effect, so the test uses a small lr and compares the UPDATES with a
+    relative tolerance (a wrong sign / missing term would be off by >= 100%)."""
     import ctypes as C
     from multiverso_b200 import _native as N
-    V, D, K, lr = 64, 300, 5, 0.01
+    V, D, K, lr = 64, 300, 5, 1e-3
     torch.manual_seed(0)
     w_in = (torch.rand(V, D, device="cuda") - 0.5) * 0.2
     w_out = (torch.rand(V, D, device="cuda") - 0.5) * 0.2
@@ -53,15 +56,19 @@ def test_sgns_fast_kernel_matches_reference(mv_device):
     a.window, a.negative, a.lr = 1, K, lr
     a.vocab, a.neg_pool, a.neg_pool_size = V, pool.data_ptr(), 1
     a.seed, a.loss_sum, a.pair_count = 1234, loss.data_ptr(), pairs.data_ptr()
+    a.variant = variant
     N.check(N.cuda_lib().mvb_sgns_train(C.byref(a), C.c_void_p(N.stream_ptr())))
     torch.cuda.synchronize()
     assert int(pairs.item()) == 8
-    assert torch.allclose(w_in.double().cpu(), ref_in, atol=2e-6), (w_in.double().cpu() - ref_in).abs().max()
-    assert torch.allclose(w_out.double().cpu(), ref_out, atol=2e-6), (w_out.double().cpu() - ref_out).abs().max()
+    d_in, d_out = w_in.double().cpu() - i0, w_out.double().cpu() - o0
+    r_in, r_out = ref_in - i0, ref_out - o0
+    assert r_in.abs().max() > 1e-5 and r_out.abs().max() > 1e-5
+    assert torch.allclose(d_in, r_in, rtol=0.05, atol=3e-7), (d_in - r_in).abs().max()
+    assert torch.allclose(d_out, r_out, rtol=0.05, atol=3e-7), (d_out - r_out).abs().max()
     assert float(loss.item()) > 0
 
 
-@pytest.mark.parametrize("mode", ["sg_ns", "cbow_ns", "sg_hs", "cbow_hs", "sg_ns_adagrad", "sg_ns_d100"])
+@pytest.mark.parametrize("mode", ["sg_ns", "cbow_ns", "sg_hs", "cbow_hs", "sg_ns_adagrad", "sg_ns_d100", "sg_ns_tma"])
 def test_wordembedding_loss_decreases(mv_device, mode):
     from multiverso_b200.models.wordembedding import (WordEmbedding, WordEmbeddingOption,
                                                       synthetic_zipf_corpus)
@@ -70,6 +77,8 @@ def test_wordembedding_loss_decreases(mv_device, mode):
                               cbow="cbow" in mode, hs="hs" in mode, use_adagrad="adagrad" in mode,
                               init_learning_rate=0.05)
     we = WordEmbedding(opt, V)
+    if mode.endswith("tma"):
+        we.kernel_variant = 10
     # a learnable corpus: word 2i is always followed by word 2i+1
     rng = np.random.default_rng(0)
     base = rng.integers(0, V // 2, size=40000) * 2

@@ -17,7 +17,7 @@ test)
   tail -15 gpurun_out/pytest_gpu.log
   ;;
 smoke)
-  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
   ;;
 bench)
   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
@@ -37,6 +37,17 @@ ncu_dense)
 import torch, multiverso_b200 as mv
 mv.init(); t = mv.MatrixTable(1000000, 512, 'float32', updater='sgd'); d = torch.ones(512000000, device='cuda')
 t.add(d); t.get(); t.add(d); t.get(); mv.shutdown()" > gpurun_out/ncu_dense.log 2>&1; echo "ncu_dense rc=$?"
+  ;;
+sweep)
+  for v in 5 3 2 1 10; do
+    MVB_SGNS_VARIANT=$v timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/sweep_v$v.json 2> gpurun_out/sweep_v$v.err; echo "variant $v rc=$? $(python -c "import json;d=json.load(open('gpurun_out/sweep_v$v.json'));print(d['value']/1e6,'Mwords/s',d['ms_per_step'],'ms', 'loss',d['config']['loss_per_pair'])" 2>&1 | tail -1)"
+  done
+  for st in 8 16; do
+    MVB_SGNS_STAGES=$st MVB_SGNS_VARIANT=10 timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/sweep_v10_s$st.json 2> gpurun_out/sweep_v10_s$st.err; echo "tma stages $st rc=$? $(python -c "import json;d=json.load(open('gpurun_out/sweep_v10_s$st.json'));print(d['value']/1e6,'Mwords/s',d['ms_per_step'],'ms')" 2>&1 | tail -1)"
+  done
+  ;;
+ncu_tma)
+  MVB_SGNS_VARIANT=10 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgns_tma -s 3 -c 1 -f -o gpurun_out/sgns_tma python bench.py --steps 2 --warmup 3 --no-table-bw > gpurun_out/ncu_sgns_tma.log 2>&1; echo "ncu_tma rc=$?"; tail -2 gpurun_out/ncu_sgns_tma.log
   ;;
 probe)
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+2)) tools/probe_symm.py > gpurun_out/probe.log 2>&1; echo "probe rc=$?"; tail -20 gpurun_out/probe.log
