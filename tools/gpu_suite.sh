@@ -39,10 +39,10 @@ mv.init(); t = mv.MatrixTable(1000000, 512, 'float32', updater='sgd'); d = torch
 t.add(d); t.get(); t.add(d); t.get(); mv.shutdown()" > gpurun_out/ncu_dense.log 2>&1; echo "ncu_dense rc=$?"
   ;;
 sweep)
-  for v in 5 3 2 1 10; do
+  for v in ${SWEEP_VARIANTS:-5 3 2 1 10}; do
     MVB_SGNS_VARIANT=$v timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/sweep_v$v.json 2> gpurun_out/sweep_v$v.err; echo "variant $v rc=$? $(python -c "import json;d=json.load(open('gpurun_out/sweep_v$v.json'));print(d['value']/1e6,'Mwords/s',d['ms_per_step'],'ms', 'loss',d['config']['loss_per_pair'])" 2>&1 | tail -1)"
   done
-  for st in 8 16; do
+  for st in ${SWEEP_STAGES:-}; do
     MVB_SGNS_STAGES=$st MVB_SGNS_VARIANT=10 timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/sweep_v10_s$st.json 2> gpurun_out/sweep_v10_s$st.err; echo "tma stages $st rc=$? $(python -c "import json;d=json.load(open('gpurun_out/sweep_v10_s$st.json'));print(d['value']/1e6,'Mwords/s',d['ms_per_step'],'ms')" 2>&1 | tail -1)"
   done
   ;;
