@@ -22,34 +22,22 @@ def init(argv: Optional[List[str]] = None, sync: Optional[bool] = None, **flags)
     Returns argv with the recognised ``-key=value`` flags removed."""
     if sync is not None:
         flags["sync"] = bool(sync)
-    rt = _rt()
-    rest = rt.start(argv, **flags)
-    if rt.backend == "host":
-        from . import host
-        host.init_backend(rt)
-    return rest
+    return _rt().start(argv, **flags)
 
 
 def shutdown(finalize_net: bool = True) -> None:
     """MV_ShutDown(finalize_net): ``False`` keeps the process group alive so the process
     can MV_Init again (Test/unittests/multiverso_env.h:15-17)."""
     rt = _rt()
-    if rt.backend == "host" and rt.started:
-        from . import host
-        host.shutdown_backend(rt, finalize_net)
-    from .parallel import collectives
-    collectives.reset()
+    if rt.backend == "device":
+        from .parallel import collectives
+        collectives.reset()
     rt.stop(finalize_net)
 
 
 def barrier() -> None:
     """MV_Barrier."""
-    rt = _rt()
-    if rt.backend == "host" and rt.started:
-        from . import host
-        host.barrier()
-    else:
-        rt.barrier()
+    _rt().barrier()
 
 
 def rank() -> int: return _rt().rank

@@ -158,6 +158,12 @@ class Runtime:
         else:
             self.backend = "host"
             self.device = torch.device("cpu")
+        if self.backend == "host":
+            # the C++ runtime (TcpNet + controller) does bootstrap, roles and ids itself
+            from . import host
+            host.init_backend(self)
+            self.started = True
+            return rest
         if self.size > 1:
             import torch.distributed as dist
             if not dist.is_initialized():
@@ -189,6 +195,13 @@ class Runtime:
     def stop(self, finalize_net: bool = True) -> None:
         """MV_ShutDown: FinishTrain in sync mode, barrier, free tables and mappings."""
         if not self.started:
+            return
+        if self.backend == "host":
+            from . import host
+            host.shutdown_backend(self, finalize_net)
+            self.tables = []
+            self.started = False
+            Runtime._inst = None
             return
         import torch
         self._finish_train()
@@ -348,7 +361,8 @@ class Runtime:
             torch.cuda.current_stream().synchronize()
             self.check_watchdog()
         else:
-            self.host_barrier()
+            from . import host
+            host.barrier()
 
     def check_watchdog(self) -> None:
         if self.err_flag is None:

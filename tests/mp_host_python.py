@@ -1,0 +1,34 @@
+"""Python API, host backend, 3 processes, BSP mode: exact-integer array / matrix / kv scenarios."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import multiverso_b200 as mv
+
+mv.init(sync=True)
+W = mv.workers_num()
+t = mv.ArrayTable(1000, "float32", init_value=np.arange(1000))
+d = np.ones(1000, np.float32)
+for it in range(1, 6):
+    t.add(d)
+    assert np.array_equal(t.get(), np.arange(1000, dtype=np.float32) + it * W)
+m = mv.MatrixTable(11, 10, "int32")
+base = (np.arange(110, dtype=np.int32) + 1).reshape(11, 10)
+for count in range(1, 4):
+    m.add(base)
+    m.add_rows([0, 1, 5, 10], base[[0, 1, 5, 10]])
+    exp = base * count * W
+    exp[[0, 1, 5, 10]] *= 2
+    assert np.array_equal(m.get(), exp)
+kv = mv.KVTable("int64", "float32")
+kv.add([1, 2, 1000003], [1.0, 2.0, 0.5])
+mv.barrier()
+assert np.allclose(kv.get([1, 2, 1000003, 9]), [W, 2 * W, 0.5 * W, 0])
+x = np.full(10, float(mv.rank() + 1), np.float64)
+mv.aggregate(x)
+assert np.allclose(x, W * (W + 1) / 2)
+mv.barrier()
+mv.shutdown()
+print("python mp ok")

@@ -1,0 +1,65 @@
+"""CPU tests of the C++ host runtime (no GPU): the reference's unit tier
+(Test/unittests/*.cpp, world size 1 loop-back) and end-to-end tier
+(`mpirun -np 4 ./multiverso.test kv|array|net|matrix|allreduce`, Test/main.cpp) re-created
+on the TCP backend with a local rank forker, plus the extra scenarios (sparse wire
+compression, async mode, stateful updaters + checkpoint)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "build", "bin", "mv_test")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    sys.path.insert(0, ROOT)
+    from multiverso_b200 import _build
+    _build.build_host()
+    assert os.path.exists(BIN)
+
+
+def run_mp(n, *cmd, timeout=120):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", str(n),
+                        "--timeout", str(timeout), "--", *cmd], capture_output=True, text=True,
+                       timeout=timeout + 30)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_native_unit_suite():
+    r = subprocess.run([BIN, "unit"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("scenario", ["net", "kv", "array", "array_async", "matrix", "sparse", "allreduce"])
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_native_multiprocess(scenario, nproc):
+    out = run_mp(nproc, BIN, scenario)
+    assert out.count("PASS") == nproc
+
+
+def test_allreduce_non_power_of_two():
+    for n in (3, 5):
+        assert run_mp(n, BIN, "allreduce").count("PASS") == n
+
+
+@pytest.mark.parametrize("updater", ["default", "sgd", "momentum_sgd", "adagrad", "dcasgd", "dcasgda"])
+def test_native_updaters_and_checkpoint(updater):
+    assert run_mp(2, BIN, f"updater:{updater}").count("PASS") == 2
+
+
+def test_backup_worker_ratio_flag():
+    # with 4 workers and 25% backup workers the BSP quorum is 3: the scenario still completes
+    out = run_mp(4, BIN, "array", "-backup_worker_ratio=25")
+    assert out.count("PASS") == 4
+
+
+def test_role_separation():
+    # rank 0 server-only, others worker-only (ps_role flag through the environment is per
+    # process, so drive it with a small Python script)
+    script = os.path.join(ROOT, "tests", "mp_host_roles.py")
+    out = run_mp(3, sys.executable, script)
+    assert out.count("roles ok") == 3
