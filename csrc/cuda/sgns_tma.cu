@@ -27,7 +27,7 @@ namespace {
 
 constexpr int kMaxRows = 8;        // input + centre + up to 6 negatives
 constexpr int kPipes = 4;          // independent producer->consumer pipelines per CTA
-constexpr int kConsPerPipe = 2;    // consumer warps per pipeline
+constexpr int kConsPerPipe = 3;    // consumer warps per pipeline
 constexpr int kConsumers = kPipes * kConsPerPipe;
 constexpr int kMetaBytes = 128;
 
@@ -108,6 +108,21 @@ MVB_DEVINL void bulk_wait_read() {
 }
 MVB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// packed fp32x2 math (Blackwell FFMA2): halves the FMA instruction count of dots / axpys
+MVB_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+MVB_DEVINL float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
 MVB_DEVINL float sigm_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 MVB_DEVINL float softplus_neg(float x) { return fmaxf(-x, 0.f) + log1pf(__expf(-fabsf(x))); }
 
@@ -126,7 +141,7 @@ sgns_tma_kernel(const __grid_constant__ TmaDev a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
+      mbar_init(empty_bar + s, kMaxRows);   // lanes 0..7 of the consumer each arrive once
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -228,6 +243,10 @@ sgns_tma_kernel(const __grid_constant__ TmaDev a) {
     }
   } else {
     // ================================ CONSUMERS =========================================
+    // Two passes over the stage keep the warp at ~60 registers (so 12 consumer warps fit):
+    // pass 1 = 1+K dots against h, pass 2 = hidden error + in-place rank-1 deltas. Lanes 0..7
+    // then each issue the TMA scatter-add of "their" row and release the slot (the empty
+    // barrier counts 8 arrivals), so the tail is 8-way parallel and nobody waits on lane 0.
     const int cw = warp - kPipes;
     const int pipe = cw % kPipes, cidx = cw / kPipes;
     uint64_t* pfull = full_bar + pipe * S;
@@ -236,95 +255,99 @@ sgns_tma_kernel(const __grid_constant__ TmaDev a) {
     const int nvec = a.dim >> 2;
     float loss_acc = 0.f;
     unsigned long long pairs_acc = 0ull;
-    int prev_slot = -1;
     for (int64_t n = cidx;; n += kConsPerPipe) {
       const int slot = (int)(n % S);
       const uint32_t round = (uint32_t)(n / S);
       unsigned char* st = pstage + (size_t)slot * a.stage_bytes;
-      StageMeta* meta = reinterpret_cast<StageMeta*>(st);
+      const StageMeta* meta = reinterpret_cast<const StageMeta*>(st);
       unsigned char* rows = st + kMetaBytes;
       mbar_wait(pfull + slot, round & 1u);
       const int n_rows = meta->n_rows;
       if (n_rows == 0) break;
-      // ---- pull rows into registers ----
-      float4 h[VPL], r[kMaxRows - 1][VPL];
+      float* my_ptr = (lane < kMaxRows) ? meta->ptr[lane] : nullptr;
+      const uint32_t used_mask = __ballot_sync(0xffffffffu, my_ptr != nullptr && lane < n_rows);
+      // ---- pass 1: dots -------------------------------------------------------------------
+      float2 h2[VPL][2];
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         const int c = lane + 32 * j;
-        h[j] = c < nvec ? *reinterpret_cast<const float4*>(rows + (size_t)c * 16) : make_float4(0, 0, 0, 0);
+        float4 t = c < nvec ? *reinterpret_cast<const float4*>(rows + (size_t)c * 16) : make_float4(0, 0, 0, 0);
+        h2[j][0] = make_float2(t.x, t.y);
+        h2[j][1] = make_float2(t.z, t.w);
       }
       float f[kMaxRows - 1];
-      bool used[kMaxRows - 1];
 #pragma unroll
       for (int k = 0; k < kMaxRows - 1; ++k) {
-        used[k] = (k + 1 < n_rows) && meta->ptr[k + 1] != nullptr;
-        float s = 0.f;
+        float2 acc = make_float2(0.f, 0.f);
+        if ((used_mask >> (k + 1)) & 1u) {
 #pragma unroll
-        for (int j = 0; j < VPL; ++j) {
-          const int c = lane + 32 * j;
-          r[k][j] = (used[k] && c < nvec)
-                        ? *reinterpret_cast<const float4*>(rows + (size_t)(k + 1) * a.row_bytes + (size_t)c * 16)
-                        : make_float4(0, 0, 0, 0);
-          s = fmaf(h[j].x, r[k][j].x, s); s = fmaf(h[j].y, r[k][j].y, s);
-          s = fmaf(h[j].z, r[k][j].z, s); s = fmaf(h[j].w, r[k][j].w, s);
+          for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nvec) {
+              float4 t = *reinterpret_cast<const float4*>(rows + (size_t)(k + 1) * a.row_bytes + (size_t)c * 16);
+              acc = ffma2(h2[j][0], make_float2(t.x, t.y), acc);
+              acc = ffma2(h2[j][1], make_float2(t.z, t.w), acc);
+            }
+          }
         }
-        f[k] = s;
+        f[k] = acc.x + acc.y;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
         for (int k = 0; k < kMaxRows - 1; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], o);
       }
-      // ---- errors, hidden error, in-place deltas ----
-      float4 herr[VPL];
-#pragma unroll
-      for (int j = 0; j < VPL; ++j) herr[j] = make_float4(0, 0, 0, 0);
+      // ---- errors (loss estimated on every 16th sample of this warp) -----------------------
+      const bool want_loss = a.loss_sum != nullptr && ((n / kConsPerPipe) & 15) == 0;
+      float g[kMaxRows - 1];
 #pragma unroll
       for (int k = 0; k < kMaxRows - 1; ++k) {
-        if (!used[k]) continue;
         const float label = (k == 0) ? 1.f : 0.f;
-        const float g = (label - sigm_fast(f[k])) * a.lr;
-        if (a.loss_sum) loss_acc += softplus_neg(k == 0 ? f[k] : -f[k]);
+        g[k] = ((used_mask >> (k + 1)) & 1u) ? (label - sigm_fast(f[k])) * a.lr : 0.f;
+        if (want_loss && ((used_mask >> (k + 1)) & 1u)) loss_acc += 16.f * softplus_neg(k == 0 ? f[k] : -f[k]);
+      }
+      // ---- pass 2: hidden error + in-place deltas -----------------------------------------
+      float2 e2[VPL][2];
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) e2[j][0] = e2[j][1] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kMaxRows - 1; ++k) {
+        if (!((used_mask >> (k + 1)) & 1u)) continue;
+        const float2 gg = make_float2(g[k], g[k]);
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
           const int c = lane + 32 * j;
-          herr[j].x = fmaf(g, r[k][j].x, herr[j].x); herr[j].y = fmaf(g, r[k][j].y, herr[j].y);
-          herr[j].z = fmaf(g, r[k][j].z, herr[j].z); herr[j].w = fmaf(g, r[k][j].w, herr[j].w);
-          if (c < nvec)
-            *reinterpret_cast<float4*>(rows + (size_t)(k + 1) * a.row_bytes + (size_t)c * 16) =
-                make_float4(g * h[j].x, g * h[j].y, g * h[j].z, g * h[j].w);
+          if (c < nvec) {
+            float4* p = reinterpret_cast<float4*>(rows + (size_t)(k + 1) * a.row_bytes + (size_t)c * 16);
+            float4 t = *p;
+            e2[j][0] = ffma2(gg, make_float2(t.x, t.y), e2[j][0]);
+            e2[j][1] = ffma2(gg, make_float2(t.z, t.w), e2[j][1]);
+            float2 d0 = fmul2(gg, h2[j][0]), d1 = fmul2(gg, h2[j][1]);
+            *p = make_float4(d0.x, d0.y, d1.x, d1.y);
+          }
         }
       }
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         const int c = lane + 32 * j;
-        if (c < nvec) *reinterpret_cast<float4*>(rows + (size_t)c * 16) = herr[j];
+        if (c < nvec)
+          *reinterpret_cast<float4*>(rows + (size_t)c * 16) = make_float4(e2[j][0].x, e2[j][0].y, e2[j][1].x, e2[j][1].y);
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        // TMA scatter-add of the sample's rows; recycle the PREVIOUS slot once its reads are done
-        for (int k = 0; k < n_rows; ++k)
-          if (meta->ptr[k]) bulk_reduce_add_s2g(meta->ptr[k], rows + (size_t)k * a.row_bytes, (uint32_t)a.row_bytes);
-        bulk_commit();
-        if (a.defer_release) {
-          if (prev_slot >= 0) {
-            bulk_wait_read<1>();
-            mbar_arrive(pempty + prev_slot);
-          }
-        } else {
+      if (lane < kMaxRows) {
+        // TMA scatter-add of this lane's row; the slot is recycled after all 8 lanes arrived
+        if ((used_mask >> lane) & 1u) {
+          bulk_reduce_add_s2g(my_ptr, rows + (size_t)lane * a.row_bytes, (uint32_t)a.row_bytes);
+          bulk_commit();
           bulk_wait_read<0>();
-          mbar_arrive(pempty + slot);
         }
+        mbar_arrive(pempty + slot);
       }
-      prev_slot = a.defer_release ? slot : -1;
       ++pairs_acc;
-      __syncwarp();
     }
+    if (lane < kMaxRows) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // adds performed
     if (lane == 0) {
-      bulk_wait_read<0>();
-      if (prev_slot >= 0) mbar_arrive(pempty + prev_slot);
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes globally performed
       if (a.loss_sum && loss_acc != 0.f) atomicAdd(a.loss_sum, loss_acc);
       if (a.pair_count && pairs_acc) atomicAdd(a.pair_count, pairs_acc);
     }
@@ -356,10 +379,14 @@ extern "C" int mvb_sgns_train_tma(const MvbSgns* h, void* stream) {
   if (stages < kConsumers) return -22;
   if (const char* e = getenv("MVB_SGNS_STAGES")) {
     int s = atoi(e) / kConsumers * kConsumers;
-    if (s >= kConsumers && s <= stages) stages = s;
+    if (s >= 2 * kConsumers && s <= stages) stages = s;
   }
+  // A producer iteration claims up to 4 consecutive slots of its pipeline at once, so a
+  // pipeline needs >= 4 slots (immediate release) or >= 4 + consumers (deferred release).
+  const int per_pipe = stages / kPipes;
+  if (per_pipe < 4) return -22;   // rows too large for the smem ring: caller falls back
   a.stages = stages;
-  a.defer_release = stages >= 2 * kConsumers ? 1 : 0;   // >= 2 slots per consumer
+  a.defer_release = 0;
   size_t smem = ((2 * stages * 8 + 127) / 128) * 128 + (size_t)stages * a.stage_bytes;
   const int vpl = (h->dim / 4 + 31) / 32;
   const int threads = 32 * (kPipes + kConsumers);

@@ -1,0 +1,41 @@
+"""Fused Get + GEMM (K2-fused): ``y = x @ W^T`` where W is a row-sharded MatrixTable.
+
+The pulled row block is never materialised: the kernel streams each W tile once from its
+owner (local or peer HBM over NVLink) with TMA into shared memory and multiplies it with
+tcgen05.mma (TF32 operands, fp32 accumulation in TMEM) against the local activations.
+Reference analogue: MatrixWorkerTable::Get followed by the application's first GEMM
+(e.g. LogReg Objective::Predict, Applications/LogisticRegression/src/objective/objective.cpp:113-120).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _native as N
+
+
+def get_gemm_supported() -> bool:
+    return bool(N.cuda_lib().mvb_get_gemm_supported())
+
+
+def get_gemm(table, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """``x``: [M, K] fp32 CUDA, ``table``: MatrixDeviceTable with num_col == K. Returns [M, num_row]."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    M, K = x.shape
+    assert K == table.num_col and table.dtype == torch.float32
+    if K % 4 != 0:
+        raise ValueError("get_gemm needs K % 4 == 0 (16-byte row pitch for TMA)")
+    Nrows = table.num_row
+    if out is None:
+        out = torch.empty(M, Nrows, dtype=torch.float32, device=x.device)
+    g = N.GetGemm()
+    g.x, g.y, g.w_cache = x.data_ptr(), out.data_ptr(), None
+    g.M, g.N, g.K = M, Nrows, K
+    g.wmap.num_row, g.wmap.num_col = Nrows, K
+    g.wmap.nservers = table.S
+    g.wmap.rows_per_server = table.rps
+    for s in range(table.S):
+        g.wmap.shard_ptrs[s] = table.shard_ptrs[s]
+    N.check(N.cuda_lib().mvb_get_gemm_fused(C.byref(g), C.c_void_p(N.stream_ptr())), "mvb_get_gemm_fused")
+    return out

@@ -63,8 +63,9 @@ def test_sgns_fast_kernel_matches_reference(mv_device, variant):
     d_in, d_out = w_in.double().cpu() - i0, w_out.double().cpu() - o0
     r_in, r_out = ref_in - i0, ref_out - o0
     assert r_in.abs().max() > 1e-5 and r_out.abs().max() > 1e-5
-    assert torch.allclose(d_in, r_in, rtol=0.05, atol=3e-7), (d_in - r_in).abs().max()
-    assert torch.allclose(d_out, r_out, rtol=0.05, atol=3e-7), (d_out - r_out).abs().max()
+    e_in = ((d_in - r_in).norm() / r_in.norm()).item()
+    e_out = ((d_out - r_out).norm() / r_out.norm()).item()
+    assert e_in < 0.05 and e_out < 0.05, (e_in, e_out)
     assert float(loss.item()) > 0
 
 
