@@ -99,7 +99,10 @@ class ClockSampler:
 def run_reference(args) -> None:
     """The reference arm: the UNMODIFIED reference from baseline/_ref through its own CLI."""
     from baseline import reference_arm
-    print(json.dumps(reference_arm.run(args)), flush=True)
+    out = reference_arm.run(args)
+    if "metric" in out or "unavailable" in out:      # ranks != 0 of a multi-rank run stay silent
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps(out), flush=True)
 
 
 def main():

@@ -439,7 +439,11 @@ extern "C" int mvb_sgns_train(const MvbSgns* h, void* stream) {
       MVB_CUDA_CHECK(cudaFuncSetAttribute(w2v_generic_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (h->n_tokens + 3) / 4;
-    int64_t cap = (int64_t)sms * 8;
+    // Hierarchical softmax funnels EVERY sample through the few inner nodes near the root;
+    // with thousands of samples in flight those rows see stale values and the accumulated
+    // step overshoots (the reference's Hogwild runs <= 16 threads). Bound the concurrency.
+    int64_t cap = h->hs ? (int64_t)sms / 4 : (int64_t)sms * 8;
+    if (const char* e = getenv("MVB_W2V_BLOCKS")) cap = atoi(e) > 0 ? atoi(e) : cap;
     if (blocks > cap) blocks = cap;
     w2v_generic_kernel<<<(int)blocks, 128, smem, st>>>(d);
   }

@@ -54,6 +54,7 @@ struct TmaDev {
   int row_bytes;      // 4 * dim
   int stage_bytes;    // kMetaBytes + rows * row_bytes (16B aligned)
   int defer_release;  // recycle a slot one sample later (needs >= 2 slots per consumer)
+  int debug;          // experiments: 1 = bulk STORE instead of reduce, 2 = no write-back at all
 };
 
 struct StageMeta {
@@ -162,14 +163,74 @@ sgns_tma_kernel(const __grid_constant__ TmaDev a) {
     const int grp = lane >> 3, sub = lane & 7;
     int64_t n_emitted = 0;
     const int64_t stride = (int64_t)gridDim.x * kPipes;
-    for (int64_t p0 = (int64_t)blockIdx.x * kPipes + pipe; p0 < a.n_tokens; p0 += stride) {
-      const int64_t q = p0 - W + lane;
-      const int tok = (lane <= 2 * W && q >= 0 && q < a.n_tokens) ? __ldg(a.tokens + q) : -1;
+    __shared__ int rid_smem[kPipes][32 * 8];          // per position: row id of (candidate, sub-lane)
+    int* my_rid = rid_smem[pipe];
+    const int64_t p_first = (int64_t)blockIdx.x * kPipes + pipe;
+    // software pipeline: the next position's token window is loaded one position ahead
+    int tok_next = -1;
+    {
+      const int64_t q = p_first - W + lane;
+      tok_next = (p_first < a.n_tokens && lane <= 2 * W && q >= 0 && q < a.n_tokens) ? __ldg(a.tokens + q) : -1;
+    }
+    for (int64_t p0 = p_first; p0 < a.n_tokens; p0 += stride) {
+      const int tok = tok_next;
+      {
+        const int64_t pn = p0 + stride, q = pn - W + lane;
+        tok_next = (pn < a.n_tokens && lane <= 2 * W && q >= 0 && q < a.n_tokens) ? __ldg(a.tokens + q) : -1;
+      }
       const int center = __shfl_sync(0xffffffffu, tok, W);
       if (center < 0) continue;
       const uint32_t brk = __ballot_sync(0xffffffffu, tok < 0);
       const uint64_t prng = hash64(a.seed ^ (uint64_t)(p0 + 1) * 0x9E3779B97F4A7C15ull);
       const int off = (int)((prng >> 16) % (uint64_t)W);
+      // ---- phase A: ALL row ids of this position in one batch -----------------------------
+      // (2W candidates x 8 sub-lanes). Every alias-table / id-map load of the position is
+      // issued back to back, so the position pays ONE dependent memory round trip instead
+      // of one per 4 candidates.
+      {
+        constexpr int kRounds = 8;                       // 8 * 32 = 256 entries >= 2*15*8
+        const int n_entries = 2 * W * 8;
+        int e_tgt[kRounds];
+        float e_pr[kRounds], e_u[kRounds];
+        int e_al[kRounds];
+#pragma unroll
+        for (int r8 = 0; r8 < kRounds; ++r8) {
+          const int e = lane + 32 * r8;
+          e_tgt[r8] = -1; e_pr[r8] = 2.f; e_u[r8] = 0.f; e_al[r8] = -1;
+          if (e < n_entries) {
+            const int ip = e >> 3, sb = e & 7;
+            if (sb >= 2 && sb < rows_per_sample) {
+              const uint64_t r = hash64(prng ^ ((uint64_t)(ip * 8 + sb) * 0xD6E8FEB86659FD93ull));
+              if (a.neg_pool) {
+                e_tgt[r8] = __ldg(a.neg_pool + (r >> 8) % (uint64_t)a.neg_pool_size);
+              } else {
+                const uint32_t idx = (uint32_t)((r >> 32) % (uint64_t)a.vocab);
+                e_u[r8] = (float)(r & 0xFFFFFF) * (1.0f / 16777216.0f);
+                e_pr[r8] = __ldg(a.alias_prob + idx);
+                e_al[r8] = __ldg(a.alias_idx + idx);
+                e_tgt[r8] = (int)idx;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int r8 = 0; r8 < kRounds; ++r8) {
+          const int e = lane + 32 * r8;
+          if (e < n_entries) {
+            const int sb = e & 7;
+            int t = -1;
+            if (sb >= 2 && sb < rows_per_sample) {
+              t = (a.neg_pool || e_u[r8] < e_pr[r8]) ? e_tgt[r8] : e_al[r8];
+              if (t == center) t = -1;                    // Parse(): target == word_idx is skipped
+              else if (a.map_out) t = __ldg(a.map_out + t);
+            } else if (sb == 1) {
+              t = a.map_out ? __ldg(a.map_out + center) : center;
+            }
+            my_rid[e] = t;                                // sb == 0 (context row) is filled below
+          }
+        }
+      }
+      __syncwarp();
       for (int base = 0; base < 2 * W; base += 4) {
         const int ip = base + grp;                        // candidate context slot of this group
         const int i = ip < W ? ip : ip + 1;               // window index (centre sits at W)
@@ -193,25 +254,9 @@ sgns_tma_kernel(const __grid_constant__ TmaDev a) {
           if (sub == 0) {
             int rid = a.map_in ? __ldg(a.map_in + ctx) : ctx;
             gptr = a.w_in + (int64_t)rid * a.ld;
-          } else if (sub == 1) {
-            int rid = a.map_out ? __ldg(a.map_out + center) : center;
-            gptr = a.w_out + (int64_t)rid * a.ld;
           } else if (sub < rows_per_sample) {
-            uint64_t r = hash64(prng ^ ((uint64_t)(ip * 8 + sub) * 0xD6E8FEB86659FD93ull));
-            int tgt;
-            if (a.neg_pool) {
-              tgt = __ldg(a.neg_pool + (r >> 8) % (uint64_t)a.neg_pool_size);
-            } else {
-              uint32_t idx = (uint32_t)((r >> 32) % (uint64_t)a.vocab);
-              float u = (float)(r & 0xFFFFFF) * (1.0f / 16777216.0f);
-              float pr = __ldg(a.alias_prob + idx);
-              int al = __ldg(a.alias_idx + idx);
-              tgt = u < pr ? (int)idx : al;
-            }
-            if (tgt != center) {
-              int rid = a.map_out ? __ldg(a.map_out + tgt) : tgt;
-              gptr = a.w_out + (int64_t)rid * a.ld;
-            }
+            const int rid = my_rid[ip * 8 + sub];
+            if (rid >= 0) gptr = a.w_out + (int64_t)rid * a.ld;
           }
           // the consumer must have released this slot (first round passes immediately)
           mbar_wait(pempty + slot, (round & 1u) ^ 1u);
@@ -337,8 +382,13 @@ sgns_tma_kernel(const __grid_constant__ TmaDev a) {
       __syncwarp();
       if (lane < kMaxRows) {
         // TMA scatter-add of this lane's row; the slot is recycled after all 8 lanes arrived
-        if ((used_mask >> lane) & 1u) {
-          bulk_reduce_add_s2g(my_ptr, rows + (size_t)lane * a.row_bytes, (uint32_t)a.row_bytes);
+        if (((used_mask >> lane) & 1u) && a.debug != 2) {
+          if (a.debug == 1)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(my_ptr), "r"(smem_u32(rows + (size_t)lane * a.row_bytes)), "r"((uint32_t)a.row_bytes)
+                         : "memory");
+          else
+            bulk_reduce_add_s2g(my_ptr, rows + (size_t)lane * a.row_bytes, (uint32_t)a.row_bytes);
           bulk_commit();
           bulk_wait_read<0>();
         }
@@ -387,6 +437,7 @@ extern "C" int mvb_sgns_train_tma(const MvbSgns* h, void* stream) {
   if (per_pipe < 4) return -22;   // rows too large for the smem ring: caller falls back
   a.stages = stages;
   a.defer_release = 0;
+  a.debug = getenv("MVB_TMA_DEBUG") ? atoi(getenv("MVB_TMA_DEBUG")) : 0;
   size_t smem = ((2 * stages * 8 + 127) / 128) * 128 + (size_t)stages * a.stage_bytes;
   const int vpl = (h->dim / 4 + 31) / 32;
   const int threads = 32 * (kPipes + kConsumers);

@@ -64,47 +64,26 @@ class WordEmbeddingOption:
 
 class HuffmanTables:
     """Device copy of the Huffman paths (HuffmanEncoder::BuildHuffmanTreeFromDict,
-    huffman_encoder.cpp:87-196): per word the inner-node ids and branch codes."""
+    huffman_encoder.cpp:87-196): per word the inner-node ids and branch codes, built by the
+    native encoder (csrc/host/applib/wordembedding_data.cpp)."""
+
+    MAX_CODE = 64
 
     def __init__(self, counts: np.ndarray, device):
-        import heapq
+        from ..apps._applib import lib
         V = len(counts)
-        heap = [(int(c), i) for i, c in enumerate(counts)]
-        heapq.heapify(heap)
-        parent = np.zeros(2 * V, dtype=np.int64)
-        binary = np.zeros(2 * V, dtype=np.int8)
-        nxt = V
-        while len(heap) > 1:
-            c1, a = heapq.heappop(heap)
-            c2, b = heapq.heappop(heap)
-            parent[a] = nxt
-            parent[b] = nxt
-            binary[b] = 1
-            heapq.heappush(heap, (c1 + c2, nxt))
-            nxt += 1
-        root = nxt - 1
-        codes, points, lens = [], [], np.zeros(V, dtype=np.int32)
-        maxlen = 1
-        for w in range(V):
-            code, point, n = [], [], w
-            while n != root and V > 1:
-                code.append(int(binary[n]))
-                n = int(parent[n])
-                point.append(n - V)
-            code.reverse()
-            point.reverse()
-            codes.append(code)
-            points.append(point)
-            lens[w] = len(code)
-            maxlen = max(maxlen, len(code))
-        self.max_code = maxlen
-        P = np.zeros((V, maxlen), dtype=np.int32)
-        Cd = np.zeros((V, maxlen), dtype=np.int8)
-        for w in range(V):
-            P[w, :lens[w]] = points[w]
-            Cd[w, :lens[w]] = codes[w]
-        self.points = torch.from_numpy(P).to(device)
-        self.codes = torch.from_numpy(Cd).to(device)
+        freq = np.ascontiguousarray(np.maximum(np.asarray(counts, dtype=np.float64), 1.0).astype(np.int64))
+        P = np.zeros((V, self.MAX_CODE), dtype=np.int32)
+        Cd = np.zeros((V, self.MAX_CODE), dtype=np.int8)
+        lens = np.zeros(V, dtype=np.int32)
+        longest = lib().MVA_HuffmanBuild(freq.ctypes.data_as(C.c_void_p), V, self.MAX_CODE,
+                                         P.ctypes.data_as(C.c_void_p), Cd.ctypes.data_as(C.c_void_p),
+                                         lens.ctypes.data_as(C.c_void_p))
+        if longest < 0:
+            Log.fatal("Huffman code longer than %d", self.MAX_CODE)
+        self.max_code = max(int(longest), 1)
+        self.points = torch.from_numpy(np.ascontiguousarray(P[:, :self.max_code])).to(device)
+        self.codes = torch.from_numpy(np.ascontiguousarray(Cd[:, :self.max_code])).to(device)
         self.lens = torch.from_numpy(lens).to(device)
 
 

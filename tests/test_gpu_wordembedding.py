@@ -76,7 +76,7 @@ def test_wordembedding_loss_decreases(mv_device, mode):
     V = 2000
     opt = WordEmbeddingOption(embeding_size=100 if mode.endswith("d100") else 64, window_size=5, negative_num=5,
                               cbow="cbow" in mode, hs="hs" in mode, use_adagrad="adagrad" in mode,
-                              init_learning_rate=0.05)
+                              init_learning_rate=0.025 if "hs" in mode else 0.05)
     we = WordEmbedding(opt, V)
     if mode.endswith("tma"):
         we.kernel_variant = 10
