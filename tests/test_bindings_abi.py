@@ -1,0 +1,70 @@
+"""Static ABI test of the language bindings that cannot be executed here (no luajit, no dotnet):
+every C symbol the Lua FFI cdef and the C# P/Invoke declarations reference must be exported by
+libmultiverso.so with the reference's C API names (include/multiverso/c_api.h:16-54)."""
+import ctypes
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+REFERENCE_C_API = [
+    "MV_Init", "MV_ShutDown", "MV_Barrier", "MV_NumWorkers", "MV_WorkerId", "MV_ServerId",
+    "MV_NewArrayTable", "MV_GetArrayTable", "MV_AddArrayTable", "MV_AddAsyncArrayTable",
+    "MV_NewMatrixTable", "MV_GetMatrixTableAll", "MV_AddMatrixTableAll", "MV_AddAsyncMatrixTableAll",
+    "MV_GetMatrixTableByRows", "MV_AddMatrixTableByRows", "MV_AddAsyncMatrixTableByRows",
+]
+
+
+def _lib():
+    from multiverso_b200 import _native
+    return _native.host_lib()
+
+
+def test_reference_c_api_symbols_exported():
+    lib = _lib()
+    for name in REFERENCE_C_API:
+        assert hasattr(lib, name), name
+
+
+def test_lua_cdef_symbols_exported():
+    src = open(os.path.join(ROOT, "binding", "lua", "init.lua")).read()
+    cdef = src[src.index("ffi.cdef[["):src.index("]]")]
+    names = re.findall(r"\b(MV_\w+)\s*\(", cdef)
+    assert set(REFERENCE_C_API) <= set(names)
+    lib = _lib()
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_csharp_pinvoke_symbols_exported():
+    src = open(os.path.join(ROOT, "binding", "csharp", "MultiversoWrapper.cs")).read()
+    names = re.findall(r"static extern \w+ (MV_\w+)\(", src)
+    assert len(names) >= 15
+    lib = _lib()
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_c_api_roundtrip_through_ctypes():
+    """The float-only reference entry points, driven exactly like the reference's Python binding."""
+    import numpy as np
+    lib = _lib()
+    lib.MV_Init(None, None)
+    h = ctypes.c_void_p()
+    lib.MV_NewArrayTable(100, ctypes.byref(h))
+    d = np.arange(100, dtype=np.float32)
+    lib.MV_AddArrayTable(h, d.ctypes.data_as(ctypes.c_void_p), 100)
+    out = np.zeros(100, np.float32)
+    lib.MV_GetArrayTable(h, out.ctypes.data_as(ctypes.c_void_p), 100)
+    assert np.array_equal(out, d)
+    m = ctypes.c_void_p()
+    lib.MV_NewMatrixTable(4, 3, ctypes.byref(m))
+    rows = (ctypes.c_int * 2)(1, 3)
+    v = np.ones(6, np.float32)
+    lib.MV_AddMatrixTableByRows(m, v.ctypes.data_as(ctypes.c_void_p), 6, rows, 2)
+    full = np.zeros(12, np.float32)
+    lib.MV_GetMatrixTableAll(m, full.ctypes.data_as(ctypes.c_void_p), 12)
+    assert full.reshape(4, 3)[[1, 3]].sum() == 6 and full.sum() == 6
+    lib.MV_ShutDownEx(0)
