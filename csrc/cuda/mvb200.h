@@ -146,6 +146,9 @@ int mvb_get_rows(int dtype, const MvbRowMap* m, const int64_t* row_ids, int64_t 
                  int64_t out_ld, void* stream);
 int mvb_add_rows_red(int dtype, const MvbRowMap* m, const int64_t* row_ids, int64_t k,
                      const void* vals, int64_t vals_ld, float sign, void* stream);
+/* fused AddDeltaParameter: red.add of (cur - old) * scale per row (fp32, num_col % 4 == 0) */
+int mvb_add_rows_delta(const MvbRowMap* m, const int64_t* row_ids, int64_t k, const float* cur,
+                       const float* old, int64_t ld, float scale, void* stream);
 /* Stateful row add applied by the OWNER on its local shard for rows in its range:
  * ids/vals may be another rank's (peer-mapped) staging. */
 int mvb_add_rows_owner(int dtype, int updater, void* shard, void* state0, void* state1,

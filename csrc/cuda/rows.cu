@@ -99,6 +99,33 @@ add_rows_red_kernel(const __grid_constant__ RowMapDev m, const int64_t* __restri
   }
 }
 
+// AddDeltaParameter fused (Applications/WordEmbedding/src/communicator.cpp:157-203): push
+// (trained - pulled) * scale for every cached row straight into the owners, no delta tensor.
+__global__ void __launch_bounds__(256)
+add_rows_delta_kernel(const __grid_constant__ RowMapDev m, const int64_t* __restrict__ ids, int64_t k,
+                      const float* __restrict__ cur, const float* __restrict__ old, int64_t ld, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nvec = (int)(m.num_col / 4);
+  for (int64_t i = warp; i < k; i += nwarps) {
+    const int64_t r = ids[i];
+    if (r < 0 || r >= m.num_row) continue;
+    int owner;
+    int64_t local;
+    locate_row(m, r, owner, local);
+    float* dst = reinterpret_cast<float*>(m.shard[owner]) + local * m.num_col;
+    const float4* a = reinterpret_cast<const float4*>(cur + i * ld);
+    const float4* b = reinterpret_cast<const float4*>(old + i * ld);
+    for (int v = lane; v < nvec; v += 32) {
+      float4 x = a[v], y = b[v];
+      x.x = (x.x - y.x) * scale; x.y = (x.y - y.y) * scale;
+      x.z = (x.z - y.z) * scale; x.w = (x.w - y.w) * scale;
+      if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f) red_add_v4_f32(dst + (int64_t)v * 4, x);
+    }
+  }
+}
+
 template <int UPD, typename T>
 __global__ void __launch_bounds__(256)
 add_rows_owner_kernel(T* __restrict__ shard, T* __restrict__ st0, T* __restrict__ st1,
@@ -267,6 +294,15 @@ extern "C" int mvb_add_rows_red(int dtype, const MvbRowMap* m, const int64_t* ro
     case MVB_I32: return add_rows_red_t<int>(m, row_ids, k, vals, vals_ld, sign, st);
   }
   return -1;
+}
+extern "C" int mvb_add_rows_delta(const MvbRowMap* m, const int64_t* row_ids, int64_t k, const float* cur,
+                                  const float* old, int64_t ld, float scale, void* stream) {
+  if (k <= 0) return 0;
+  if (m->num_col % 4 || ld % 4) return -9;
+  RowMapDev d = to_dev(m);
+  add_rows_delta_kernel<<<grid_for_warps(k, 256), 256, 0, (cudaStream_t)stream>>>(d, row_ids, k, cur, old, ld, scale);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 extern "C" int mvb_add_rows_owner(int dtype, int updater, void* shard, void* state0, void* state1,
                                   int64_t row_lo, int64_t row_hi, int64_t num_col,

@@ -28,6 +28,7 @@
 #include "multiverso/table/matrix.h"
 #include "multiverso/table/matrix_table.h"
 #include "multiverso/table/sparse_matrix_table.h"
+#include "multiverso/table/sparse_table.h"
 #include "multiverso/util/allocator.h"
 #include "multiverso/util/async_buffer.h"
 #include "multiverso/util/configure.h"
@@ -456,6 +457,38 @@ static void TestUpdatersAndCheckpoint(const std::string& updater) {
   MV_SetFlag<std::string>("updater_type", "default");
 }
 
+static void TestAppTables() {   // LogReg SparseTable / FTRLTable (sparse_table.h, ftrl_sparse_table.h)
+  MV_Init();
+  const int W = MV_NumWorkers();
+  auto* t = MV_CreateTable(SparseTableOption<float>(1000003));
+  auto* f = MV_CreateTable(FTRLTableOption<float>(5000));
+  if (t) {
+    std::vector<size_t> keys = {0, 7, 999, 500001, 1000002};
+    std::vector<float> vals = {1.f, 2.f, 3.f, 4.f, 5.f}, got(5, -1.f);
+    t->Add(keys.data(), vals.data(), keys.size());
+    MV_Barrier();
+    t->Get(keys.data(), keys.size(), got.data());
+    for (size_t i = 0; i < keys.size(); ++i) EXPECT(got[i] == -vals[i] * W);   // server subtracts
+    std::vector<size_t> ak;
+    std::vector<float> av;
+    t->GetAll(&ak, &av);
+    EXPECT(ak.size() == keys.size() && av.size() == keys.size());
+    std::vector<size_t> fk = {3, 4999};
+    std::vector<FTRLEntry<float>> fv = {{1.f, 2.f}, {0.5f, 0.25f}}, fg(2);
+    f->Add(fk.data(), fv.data(), 2);
+    MV_Barrier();
+    f->Get(fk.data(), 2, fg.data());
+    EXPECT(fg[0].z == -1.f * W && fg[0].n == -2.f * W && fg[1].n == -0.25f * W);
+  } else {
+    MV_Barrier();
+    MV_Barrier();
+  }
+  MV_Barrier();
+  delete t;
+  delete f;
+  MV_ShutDown();
+}
+
 int main(int argc, char* argv[]) {
   if (argc < 2) {
     fprintf(stderr, "usage: mv_test unit|kv|array|array_async|net|matrix|sparse|allreduce|updater:<name> [-flag=value ...]\n");
@@ -471,6 +504,7 @@ int main(int argc, char* argv[]) {
   else if (which == "matrix") TestMatrix(false);
   else if (which == "sparse") TestMatrix(true);
   else if (which == "allreduce") TestAllreduce();
+  else if (which == "apptables") TestAppTables();
   else if (which.rfind("updater:", 0) == 0) TestUpdatersAndCheckpoint(which.substr(8));
   else { fprintf(stderr, "unknown test %s\n", which.c_str()); return 2; }
   printf("[mv_test %s] %s\n", which.c_str(), g_fail ? "FAIL" : "PASS");

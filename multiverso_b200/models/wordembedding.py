@@ -216,6 +216,7 @@ class WordEmbedding:
         # RequestParameter (communicator.cpp:117-155): pull the block's rows
         cache_in = self.input_table.get_rows(in_ids)
         cache_out = self.output_table.get_rows(out_ids)
+        self.kernel_launches += 2
         old_in, old_out = cache_in.clone(), cache_out.clone()
         g2i = g2o = None
         if o.use_adagrad:
@@ -227,11 +228,19 @@ class WordEmbedding:
                          neg_pool, compute_loss)
         # AddDeltaParameter (communicator.cpp:206-249): delta = (trained - pulled) / W
         inv = 1.0 / self.W
-        self.input_table.add_rows(in_ids, (cache_in - old_in) * inv)
-        self.output_table.add_rows(out_ids, (cache_out - old_out) * inv)
-        if o.use_adagrad:
-            self.g2_in.add_rows(in_ids, (g2i - old_g2i) * inv)
-            self.g2_out.add_rows(out_ids, (g2o - old_g2o) * inv)
+        if D % 4 == 0:
+            self.input_table.add_rows_delta(in_ids, cache_in, old_in, inv)
+            self.output_table.add_rows_delta(out_ids, cache_out, old_out, inv)
+            if o.use_adagrad:
+                self.g2_in.add_rows_delta(in_ids, g2i, old_g2i, inv)
+                self.g2_out.add_rows_delta(out_ids, g2o, old_g2o, inv)
+            self.kernel_launches += 2
+        else:
+            self.input_table.add_rows(in_ids, (cache_in - old_in) * inv)
+            self.output_table.add_rows(out_ids, (cache_out - old_out) * inv)
+            if o.use_adagrad:
+                self.g2_in.add_rows(in_ids, (g2i - old_g2i) * inv)
+                self.g2_out.add_rows(out_ids, (g2o - old_g2o) * inv)
 
     # ------------------------------------------------------------------ word count (KV)
     def add_word_count(self, n: int) -> None:

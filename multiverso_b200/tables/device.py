@@ -435,6 +435,23 @@ class MatrixDeviceTable(DenseDeviceTable):
         self._keep_rows = (ids, vals)
         return self._record()
 
+    def add_rows_delta(self, row_ids: torch.Tensor, cur: torch.Tensor, old: torch.Tensor, scale: float) -> None:
+        """Fused AddDeltaParameter: rows += (cur - old) * scale, pushed one-sided into the owners
+        (default/sgd updaters, fp32, num_col % 4 == 0). No delta tensor is materialised."""
+        assert self.updater in (N.UPD_DEFAULT, N.UPD_SGD) and self.dtype == torch.float32
+        ids = self._ids(row_ids)
+        k = ids.numel()
+        sign = -1.0 if self.updater == N.UPD_SGD else 1.0
+        with monitor("WORKER_TABLE_ADD_ROWS", cuda=True, nbytes=k * self.num_col * self.esz):
+            N.check(N.cuda_lib().mvb_add_rows_delta(C.byref(self._rowmap), C.c_void_p(ids.data_ptr()),
+                                                    C.c_int64(k), C.c_void_p(cur.data_ptr()),
+                                                    C.c_void_p(old.data_ptr()), C.c_int64(cur.stride(0)),
+                                                    C.c_float(sign * scale), C.c_void_p(N.stream_ptr())),
+                    "mvb_add_rows_delta")
+            if self.is_sparse:
+                self._mark_stale(ids)
+        self._keep_rows = (ids, cur, old)
+
     def add_row(self, row_id: int, values, option: Optional[AddOption] = None) -> None:
         self.add_rows([row_id], torch.as_tensor(values).view(1, -1), option)
 

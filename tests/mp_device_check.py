@@ -123,6 +123,17 @@ def scenario_async():
         y = torch.full((n_el,), float(r + 1), device="cuda")
         mv.aggregate(y)
         check(f"aggregate_f32_{n_el}", torch.equal(y, torch.full((n_el,), W * (W + 1) / 2.0, device="cuda")))
+    # fused Get+GEMM with the W tiles streamed from peer shards by TMA (tcgen05 / TMEM)
+    from multiverso_b200.ops import get_gemm
+    wt = mv.MatrixTable(1000, 256, "float32", min_value=-1.0, max_value=1.0, seed=3)
+    mv.barrier()
+    Wfull = wt.get().view(1000, 256).clone()
+    xg = torch.randn(300, 256, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    yg = get_gemm(wt, xg)
+    torch.cuda.synchronize()
+    ref = xg.double() @ Wfull.double().T
+    check("get_gemm_peer_tma", (yg.double() - ref).abs().max().item() < 4e-3 * 16 * 4, str((yg.double() - ref).abs().max().item()))
+    mv.barrier()
     # distributed WordEmbedding block (block mode)
     from multiverso_b200.models.wordembedding import WordEmbedding, WordEmbeddingOption, synthetic_zipf_corpus
     we = WordEmbedding(WordEmbeddingOption(embeding_size=300, init_learning_rate=0.01), 200000)

@@ -34,7 +34,7 @@ def test_native_unit_suite():
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("scenario", ["net", "kv", "array", "array_async", "matrix", "sparse", "allreduce"])
+@pytest.mark.parametrize("scenario", ["net", "kv", "array", "array_async", "matrix", "sparse", "allreduce", "apptables"])
 @pytest.mark.parametrize("nproc", [2, 4])
 def test_native_multiprocess(scenario, nproc):
     out = run_mp(nproc, BIN, scenario)

@@ -46,6 +46,15 @@ sweep)
     MVB_SGNS_STAGES=$st MVB_SGNS_VARIANT=10 timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/sweep_v10_s$st.json 2> gpurun_out/sweep_v10_s$st.err; echo "tma stages $st rc=$? $(python -c "import json;d=json.load(open('gpurun_out/sweep_v10_s$st.json'));print(d['value']/1e6,'Mwords/s',d['ms_per_step'],'ms')" 2>&1 | tail -1)"
   done
   ;;
+extra)
+  if [ "$NG" -gt 1 ]; then L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+5))"; else L="python"; fi
+  timeout 600 $L bench/matrix_bw.py > gpurun_out/matrix_bw.log 2>&1; echo "matrix_bw rc=$?"; grep '^{' gpurun_out/matrix_bw.log | tail -1 | cut -c1-600
+  timeout 600 $L bench/matrix_bw.py --array-gb 4 --updater momentum_sgd > gpurun_out/array_bw.log 2>&1; echo "array_bw rc=$?"; grep '^{' gpurun_out/array_bw.log | tail -1 | cut -c1-600
+  timeout 600 $L bench/logreg_sparse.py > gpurun_out/logreg_sparse.log 2>&1; echo "logreg_sparse rc=$?"; grep '^{' gpurun_out/logreg_sparse.log | tail -1 | cut -c1-400
+  ;;
+refarm)
+  timeout 1500 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_n1.json
+  ;;
 tma_debug)
   for dbg in 0 1 2; do
     MVB_TMA_DEBUG=$dbg MVB_SGNS_VARIANT=10 timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/tma_dbg$dbg.json 2> gpurun_out/tma_dbg$dbg.err; echo "tma debug $dbg rc=$? $(python -c "import json;d=json.load(open('gpurun_out/tma_dbg$dbg.json'));print(d['value']/1e6,'Mwords/s',d['ms_per_step'],'ms')" 2>&1 | tail -1)"
