@@ -108,3 +108,13 @@ def test_multiprocess_python_api():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", "3", "--", sys.executable,
                         script], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0 and r.stdout.count("python mp ok") == 3, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_compat_binding_suite_single_and_multi_process():
+    """binding/python/multiverso (drop-in for the reference binding) at 1 and 2 processes."""
+    suite = os.path.join(ROOT, "binding", "python", "multiverso", "tests", "test_multiverso.py")
+    r = subprocess.run([sys.executable, suite], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", "2", "--", sys.executable, suite],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
