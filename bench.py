@@ -151,6 +151,7 @@ def main():
     for i in range(W):
         step_device(i)
     sync_all()
+    mv.Dashboard.reset()
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
@@ -165,6 +166,7 @@ def main():
     launches = we.kernel_launches - launches0
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
+    monitors = mv.Dashboard.snapshot()
     pairs = int(we.pairs.item())
     loss_per_pair = float(we.loss.item()) / max(pairs, 1)
 
@@ -209,7 +211,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "words/s", "h2d_bytes_per_step": B * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / K},
             "gpu_launches": launches,
-            "extra": extra,
+            "extra": dict(extra, monitors_device_arm=monitors),
         }
         print(json.dumps(out), flush=True)
     mv.shutdown()

@@ -5,6 +5,7 @@ from .api import (aggregate, barrier, dashboard_display, init, is_master_worker,
                   net_connect, net_finalize, num_servers, num_workers, rank, server_id,
                   server_id_to_rank, set_flag, shutdown, size, worker_id, worker_id_to_rank,
                   workers_num)
+from . import ops, runtime  # noqa: F401
 from .tables import (AddOption, ArrayTable, ArrayTableOption, GetOption, KVTable, KVTableOption,
                      MatrixOption, MatrixTable, MatrixTableOption, SparseMatrixTable,
                      SparseMatrixTableOption, create_table)

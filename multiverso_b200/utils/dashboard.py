@@ -95,6 +95,16 @@ class _Dashboard:
             Log.info("%s", self._record[name].info_string())
         Log.info("---------------------------------------------------------------")
 
+    def snapshot(self) -> dict:
+        """{name: {count, total_ms, avg_ms, gbs}} of every monitor (device-timed where applicable)."""
+        out = {}
+        for name, m in sorted(self._record.items()):
+            m.info_string()   # drains finished CUDA events
+            out[name] = {"count": m.count, "total_ms": round(m.elapse_ms, 3), "avg_ms": round(m.average(), 4)}
+            if m.bytes and m.elapse_ms > 0:
+                out[name]["gbs"] = round(m.bytes / m.elapse_ms / 1e6, 1)
+        return out
+
     def reset(self) -> None:
         with self._lock:
             self._record.clear()
