@@ -172,6 +172,32 @@ __global__ void __launch_bounds__(256) allreduce_twoshot_finish(const __grid_con
     for (int64_t i = nvec * VEC + threadIdx.x; i < a.n; i += blockDim.x) a.out[i] = src[i];
 }
 
+// NVLS two-shot: rank r reduces slice r IN THE SWITCH (multimem.ld_reduce on the multicast
+// address) and broadcasts it with one multimem.st; per-GPU NVLink traffic is n/W in + n/W out
+// instead of (W-1)/W * n each way.
+__global__ void __launch_bounds__(256)
+allreduce_nvls_kernel(const __grid_constant__ ArDev<float> a, float* __restrict__ mc) {
+  handshake_begin(a);
+  const int64_t nvec_total = a.n / 4;
+  const int64_t per = (nvec_total + a.world - 1) / a.world;
+  const int64_t lo = per * a.me;
+  int64_t hi = lo + per;
+  if (hi > nvec_total) hi = nvec_total;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += stride) {
+    float4 r = multimem_ld_reduce_add_v4_f32(mc + v * 4);
+    multimem_st_v4_f32(mc + v * 4, r);
+  }
+  if (a.me == 0 && blockIdx.x == 0) {
+    for (int64_t i = nvec_total * 4 + threadIdx.x; i < a.n; i += blockDim.x) {
+      float s = a.bufs[0][i];
+      for (int r = 1; r < a.world; ++r) s += a.bufs[r][i];
+      for (int r = 0; r < a.world; ++r) a.bufs[r][i] = s;
+    }
+  }
+  handshake_end(a);
+}
+
 template <typename T>
 ArDev<T> to_dev(const MvbAllreduce* h) {
   ArDev<T> a{};
@@ -229,6 +255,25 @@ int dispatch(const MvbAllreduce* h, bool twoshot, void* stream) {
 }
 
 }  // namespace
+
+extern "C" int mvb_allreduce_nvls(const MvbAllreduce* h, void* multicast_ptr, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->dtype != MVB_F32 || multicast_ptr == nullptr) return -40;
+  if (h->world < 2 || h->world > MVB_MAX_RANKS) return -3;
+  ArDev<float> a = to_dev<float>(h);
+  int64_t work = h->n / 4 / h->world;
+  int64_t blocks = (work + 255) / 256;
+  int64_t cap = (int64_t)mvb_num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  allreduce_nvls_kernel<<<(int)blocks, 256, 0, st>>>(a, (float*)multicast_ptr);
+  int64_t b2 = (h->n / 4 + 255) / 256;
+  if (b2 > cap * 2) b2 = cap * 2;
+  if (b2 < 1 || a.out == a.bufs[a.me]) b2 = 1;
+  allreduce_twoshot_finish<float><<<(int)b2, 256, 0, st>>>(a);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int mvb_allreduce_oneshot(const MvbAllreduce* a, void* stream) {
   return dispatch(a, false, stream);

@@ -26,6 +26,7 @@ struct DenseAddDev {
   int W;
   uint32_t mask;
   const T* delta[MVB_MAX_RANKS];
+  const T* delta_mc;     // NVLS multicast view of the staging buffers (or nullptr)
   MvbAddOpt opts[MVB_MAX_RANKS];
   float scale, clip;
   MvbPeers pads;
@@ -116,6 +117,21 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     const int64_t i = v * VEC;
+    if constexpr (std::is_same<T, float>::value && VEC == 4 && (UPD == MVB_UPD_DEFAULT || UPD == MVB_UPD_SGD)) {
+      if (a.delta_mc != nullptr) {
+        // NVLS: one multimem.ld_reduce returns the sum over every worker's staging buffer,
+        // reduced inside the NVSwitch (ingress = 1/W of the P2P pull); linear updaters only.
+        float4 sum = multimem_ld_reduce_add_v4_f32(a.delta_mc + a.shard_off + i);
+        Pack<T, VEC> d = pk_load<T, VEC>(a.shard + i);
+        T z0 = 0, z1 = 0;
+        U::Apply(d.v[0], prep_delta<T>(sum.x, a.scale, a.clip), z0, z1, a.opts[0]);
+        U::Apply(d.v[1], prep_delta<T>(sum.y, a.scale, a.clip), z0, z1, a.opts[0]);
+        U::Apply(d.v[2], prep_delta<T>(sum.z, a.scale, a.clip), z0, z1, a.opts[0]);
+        U::Apply(d.v[3], prep_delta<T>(sum.w, a.scale, a.clip), z0, z1, a.opts[0]);
+        pk_store<T, VEC>(a.shard + i, d);
+        continue;
+      }
+    }
     Pack<T, VEC> g[MVB_MAX_RANKS];
 #pragma unroll
     for (int w = 0; w < MVB_MAX_RANKS; ++w) {
@@ -215,6 +231,7 @@ int launch_add(const MvbDenseAdd* h, cudaStream_t st) {
     a.worker_rank[w] = h->worker_rank[w];
     if (w < h->nworkers && !aligned16<T>(h->delta_ptrs[w])) vec_ok = false;
   }
+  a.delta_mc = (const T*)h->delta_multicast;
   a.scale = h->scale;
   a.clip = h->clip;
   a.has_pads = h->pads != nullptr;

@@ -87,6 +87,8 @@ typedef struct MvbDenseAdd {
   int nworkers;
   uint32_t worker_mask;   /* which workers contribute    */
   const void* delta_ptrs[MVB_MAX_RANKS]; /* indexed by worker id */
+  const void* delta_multicast;  /* optional NVLS multicast mapping of the staging buffers:
+                                   default/sgd fp32 adds then reduce in the switch */
   MvbAddOpt opts[MVB_MAX_RANKS];         /* per worker          */
   float scale;            /* delta pre-scale (1 = none)  */
   float clip;             /* |delta| clip, 0 = off       */
@@ -199,6 +201,8 @@ typedef struct MvbAllreduce {
 } MvbAllreduce;
 int mvb_allreduce_oneshot(const MvbAllreduce* a, void* stream);
 int mvb_allreduce_twoshot(const MvbAllreduce* a, void* stream);
+/* NVLS: in-switch reduction through the multicast mapping of the staging buffers (fp32) */
+int mvb_allreduce_nvls(const MvbAllreduce* a, void* multicast_ptr, void* stream);
 
 /* ---- WordEmbedding (K7) -------------------------------------------------------- */
 typedef struct MvbSgns {

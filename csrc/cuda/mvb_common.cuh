@@ -100,6 +100,22 @@ MVB_DEVINL void red_add_s32(int* p, int v) {
   asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// NVLS (NVSwitch in-network reduction): one load on the MULTICAST address returns the sum of
+// the same location in every rank's copy; one store replicates to every rank's copy.
+MVB_DEVINL float4 multimem_ld_reduce_add_v4_f32(const void* mc_ptr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_ptr)
+               : "memory");
+  return r;
+}
+MVB_DEVINL void multimem_st_v4_f32(void* mc_ptr, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_ptr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 template <typename T>
 struct VecOf;  // 16-byte vector of T
 template <>

@@ -50,7 +50,7 @@ def aggregate(data: torch.Tensor, algo: str = "auto") -> torch.Tensor:
             rt.barrier()
             rt.release_symm(st.staging)
         st.cap = max(nbytes, 1 << 20)
-        st.staging = rt.alloc_symm(st.cap)
+        st.staging = rt.alloc_multicast(st.cap) or rt.alloc_symm(st.cap)
         st.counter = rt.done_counter_ptr()
     ch = 1  # channels 1 (ready) and 2 (done) are reserved for aggregate
     stream = C.c_void_p(N.stream_ptr())
@@ -73,8 +73,13 @@ def aggregate(data: torch.Tensor, algo: str = "auto") -> torch.Tensor:
     a.err_flag = rt.err_flag.data_ptr()
     a.done_counter = st.counter
     a.timeout_s = float(FLAGS.get("barrier_timeout_s"))
-    two = (algo == "twoshot") or (algo == "auto" and nbytes > TWO_SHOT_BYTES)
+    two = (algo == "twoshot") or (algo in ("auto", "nvls") and nbytes > TWO_SHOT_BYTES)
+    mc = getattr(st.staging, "multicast_ptr", 0)
+    use_nvls = bool(mc) and data.dtype == torch.float32 and (algo == "nvls" or (algo == "auto" and two))
     with monitor("MV_AGGREGATE", cuda=True, nbytes=nbytes):
-        fn = lib.mvb_allreduce_twoshot if two else lib.mvb_allreduce_oneshot
-        N.check(fn(C.byref(a), stream), "mvb_allreduce")
+        if use_nvls:
+            N.check(lib.mvb_allreduce_nvls(C.byref(a), C.c_void_p(mc), stream), "mvb_allreduce_nvls")
+        else:
+            fn = lib.mvb_allreduce_twoshot if two else lib.mvb_allreduce_oneshot
+            N.check(fn(C.byref(a), stream), "mvb_allreduce")
     return data

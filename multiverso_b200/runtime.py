@@ -102,6 +102,45 @@ class SymmBuffer:
             self.local_ptr = 0
 
 
+class McBuffer:
+    """A symmetric allocation that is ALSO bound to an NVLS multicast object, so kernels can use
+    ``multimem.ld_reduce`` / ``multimem.st`` on ``multicast_ptr`` (in-switch reduction / broadcast).
+    Allocated through torch.distributed._symmetric_memory (CUDA VMM + cuMulticast*); same
+    ``ptrs`` / ``tensor`` interface as SymmBuffer. Raises if the platform has no multicast."""
+
+    def __init__(self, rt: "Runtime", nbytes: int):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rt = rt
+        self.nbytes = max(int(nbytes), 16)
+        self._t = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=rt.device)
+        self._hdl = symm_mem.rendezvous(self._t, dist.group.WORLD.group_name)
+        self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        self.local_ptr = self.ptrs[rt.rank]
+        self.multicast_ptr = int(self._hdl.multicast_ptr or 0)
+        if not self.multicast_ptr:
+            raise RuntimeError("no NVLS multicast support")
+        self._t.zero_()
+
+    def tensor(self, dtype, numel: Optional[int] = None, offset_bytes: int = 0):
+        import torch
+        esz = torch.empty((), dtype=dtype).element_size()
+        if numel is None:
+            numel = (self.nbytes - offset_bytes) // esz
+        return self._t[offset_bytes:offset_bytes + numel * esz].view(dtype)
+
+    def ptr_array(self):
+        arr = N.VP8()
+        for r in range(N.MAX_RANKS):
+            arr[r] = self.ptrs[r] if r < len(self.ptrs) else None
+        return arr
+
+    def free(self):
+        self._t = None
+        self._hdl = None
+
+
 class Runtime:
     """Singleton process state (``Zoo::Get()``)."""
 
@@ -335,6 +374,21 @@ class Runtime:
         b = SymmBuffer(self, nbytes)
         self._symm.append(b)
         return b
+
+    def alloc_multicast(self, nbytes: int):
+        """Symmetric + NVLS multicast allocation, or None when NVLS is unavailable / disabled.
+        Collective: every rank must call it in the same order (all succeed or all fail)."""
+        if self.size == 1 or not bool(FLAGS.get("nvls")) or getattr(self, "_nvls_broken", False):
+            return None
+        try:
+            b = McBuffer(self, nbytes)
+        except Exception as e:   # no multicast object / rendezvous unsupported: fall back to P2P
+            self._nvls_broken = True
+            Log.info("NVLS multicast unavailable (%s): using the P2P kernels", repr(e)[:120])
+            return None
+        ok = all(self.all_gather_object(True))
+        self._symm.append(b)
+        return b if ok else None
 
     def release_symm(self, b: SymmBuffer) -> None:
         if b in self._symm:

@@ -142,7 +142,9 @@ class DenseDeviceTable(_AsyncOps):
     # ------------------------------------------------------------------ helpers
     def _stage_buf(self):
         if not self._stage:
-            self._stage = [self.rt.alloc_symm(self.size * self.esz) for _ in range(2)]
+            linear = self.updater in (N.UPD_DEFAULT, N.UPD_SGD) and self.dtype == torch.float32
+            self._stage = [(self.rt.alloc_multicast(self.size * self.esz) if linear else None)
+                           or self.rt.alloc_symm(self.size * self.esz) for _ in range(2)]
         b = self._stage[self._stage_idx]
         self._stage_idx ^= 1
         return b
@@ -194,7 +196,10 @@ class DenseDeviceTable(_AsyncOps):
                 # worker's option is its own -- gather the 20-byte structs once per call only
                 # when a stateful updater needs per-worker learning rates.
                 ptrs = [buf.ptrs[rt.worker_id_to_rank(w)] for w in range(self.W)]
-                self._launch_fused(ptrs, opts, pads=True)
+                # NVLS: when the staging is multicast-bound and every rank is a worker the owner
+                # reduces its slice inside the switch instead of pulling W copies
+                mc = getattr(buf, "multicast_ptr", 0) if rt.num_workers() == rt.size else 0
+                self._launch_fused(ptrs, opts, pads=True, multicast=mc)
             else:
                 src = self._as_device(delta)
                 sign = -1.0 if self.updater == N.UPD_SGD else 1.0
@@ -208,7 +213,7 @@ class DenseDeviceTable(_AsyncOps):
         return self._record()
 
     def _launch_fused(self, delta_ptrs: Sequence[int], opts: Sequence[AddOption], pads: bool,
-                      serve_only: bool = False) -> None:
+                      serve_only: bool = False, multicast: int = 0) -> None:
         rt, lib = self.rt, N.cuda_lib()
         a = N.DenseAdd()
         a.dtype, a.updater = self.dcode, self.updater
@@ -225,6 +230,7 @@ class DenseDeviceTable(_AsyncOps):
             a.opts[w].worker_id = w
             a.worker_rank[w] = rt.worker_id_to_rank(w) if rt.size > 1 else 0
         a.scale, a.clip = 1.0, 0.0
+        a.delta_multicast = multicast or None
         self._pads_arr = rt.pads_array() if pads else None
         a.pads = C.cast(self._pads_arr, C.POINTER(C.c_void_p)) if pads else None
         a.me, a.world = rt.rank, rt.size
@@ -283,6 +289,19 @@ class DenseDeviceTable(_AsyncOps):
         it never gates a BSP epoch again (src/server.cpp:190-213)."""
         rt, lib = self.rt, N.cuda_lib()
         self._finished = True
+        if rt.is_worker() and any(getattr(b, "multicast_ptr", 0) for b in self._stage):
+            # NVLS adds sum EVERY rank's staging in the switch and cannot mask a finished worker:
+            # once all owners have consumed our last Add, leave zeros behind.
+            if self.add_epoch > 0:
+                mask = 0
+                for s_ in range(self.S):
+                    mask |= 1 << rt.server_id_to_rank(s_)
+                N.check(lib.mvb_wait(rt.pads_array(), rt.rank, rt.size, self.ch_done, C.c_uint64(self.add_epoch),
+                                     C.c_uint32(mask), C.c_void_p(rt.err_flag.data_ptr()),
+                                     C.c_double(float(FLAGS.get("barrier_timeout_s"))),
+                                     C.c_void_p(N.stream_ptr())), "mvb_wait")
+            for b in self._stage:
+                b.tensor(torch.uint8).zero_()
         if rt.is_worker():
             N.check(lib.mvb_signal(rt.pads_array(), rt.rank, rt.size, self.ch_ready,
                                    C.c_uint64(N.EPOCH_FIN), C.c_void_p(N.stream_ptr())), "mvb_signal")

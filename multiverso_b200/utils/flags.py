@@ -27,6 +27,7 @@ _DEFAULTS: Dict[str, Any] = {
     "barrier_timeout_s": 120.0,   # watchdog on device-side spins
     "kv_capacity": 1 << 20,       # slots per KV shard
     "async_one_sided": True,      # async mode: stateless updaters push with red.add
+    "nvls": True,                 # use NVSwitch multicast (multimem.*) when the platform offers it
 }
 
 _TEXT: Dict[str, str] = {

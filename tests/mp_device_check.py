@@ -123,6 +123,10 @@ def scenario_async():
         y = torch.full((n_el,), float(r + 1), device="cuda")
         mv.aggregate(y)
         check(f"aggregate_f32_{n_el}", torch.equal(y, torch.full((n_el,), W * (W + 1) / 2.0, device="cuda")))
+    z = torch.full((5_000_000,), float(r + 1), device="cuda")
+    from multiverso_b200.parallel import aggregate as _agg
+    _agg(z, algo="nvls")
+    check("aggregate_nvls_or_fallback", torch.equal(z, torch.full((5_000_000,), W * (W + 1) / 2.0, device="cuda")))
     # fused Get+GEMM with the W tiles streamed from peer shards by TMA (tcgen05 / TMEM)
     from multiverso_b200.ops import get_gemm
     wt = mv.MatrixTable(1000, 256, "float32", min_value=-1.0, max_value=1.0, seed=3)

@@ -24,8 +24,8 @@ bench)
   ;;
 mp)
   if [ "$NG" -gt 1 ]; then
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $PORT tests/mp_device_check.py > gpurun_out/mp_check.log 2>&1; echo "mp rc=$?"; grep -E "PASS|FAIL|Error|error" gpurun_out/mp_check.log | head -20
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+1)) bench.py --gpus $NG --steps 10 --warmup 3 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err; echo "bench$NG rc=$?"; cat gpurun_out/bench_n$NG.json; tail -5 gpurun_out/bench_n$NG.err
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $PORT tests/mp_device_check.py > gpurun_out/mp_check.log 2>&1; echo "mp rc=$?"; grep -E "PASS|FAIL|Error|error" gpurun_out/mp_check.log | head -20
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+1)) bench.py --gpus $NG --steps 10 --warmup 3 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err; echo "bench$NG rc=$?"; cat gpurun_out/bench_n$NG.json; tail -5 gpurun_out/bench_n$NG.err
   fi
   ;;
 ncu)
@@ -48,9 +48,9 @@ sweep)
   ;;
 extra)
   if [ "$NG" -gt 1 ]; then L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+5))"; else L="python"; fi
-  timeout 600 $L bench/matrix_bw.py > gpurun_out/matrix_bw.log 2>&1; echo "matrix_bw rc=$?"; grep '^{' gpurun_out/matrix_bw.log | tail -1 | cut -c1-600
-  timeout 600 $L bench/matrix_bw.py --array-gb 4 --updater momentum_sgd > gpurun_out/array_bw.log 2>&1; echo "array_bw rc=$?"; grep '^{' gpurun_out/array_bw.log | tail -1 | cut -c1-600
-  timeout 600 $L bench/logreg_sparse.py > gpurun_out/logreg_sparse.log 2>&1; echo "logreg_sparse rc=$?"; grep '^{' gpurun_out/logreg_sparse.log | tail -1 | cut -c1-400
+  timeout 300 $L bench/matrix_bw.py > gpurun_out/matrix_bw.log 2>&1; echo "matrix_bw rc=$?"; grep '^{' gpurun_out/matrix_bw.log | tail -1 | cut -c1-600
+  timeout 300 $L bench/matrix_bw.py --array-gb 4 --updater momentum_sgd > gpurun_out/array_bw.log 2>&1; echo "array_bw rc=$?"; grep '^{' gpurun_out/array_bw.log | tail -1 | cut -c1-600
+  timeout 300 $L bench/logreg_sparse.py > gpurun_out/logreg_sparse.log 2>&1; echo "logreg_sparse rc=$?"; grep '^{' gpurun_out/logreg_sparse.log | tail -1 | cut -c1-400
   ;;
 refarm)
   timeout 1500 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_n1.json
