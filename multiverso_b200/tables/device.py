@@ -142,7 +142,8 @@ class DenseDeviceTable(_AsyncOps):
     # ------------------------------------------------------------------ helpers
     def _stage_buf(self):
         if not self._stage:
-            linear = self.updater in (N.UPD_DEFAULT, N.UPD_SGD) and self.dtype == torch.float32
+            linear = (self.updater in (N.UPD_DEFAULT, N.UPD_SGD) and self.dtype == torch.float32
+                      and bool(FLAGS.get("nvls_add")))
             self._stage = [(self.rt.alloc_multicast(self.size * self.esz) if linear else None)
                            or self.rt.alloc_symm(self.size * self.esz) for _ in range(2)]
         b = self._stage[self._stage_idx]
