@@ -461,7 +461,102 @@ push_red_kernel(const T* __restrict__ delta, const __grid_constant__ PushDev p, 
   for (int64_t i = tid; i < len; i += stride) red_add(dst + i, (T)(src[i] * (T)sign));
 }
 
+// ---------------------------------------------------------------------------
+// one-sided push for STATEFUL updaters (async PS): the worker applies its own delta on the
+// owner's shard AND state through the peer mapping (remote read-modify-write). Per-worker
+// state slabs (AdaGrad / DC-ASGD) are touched by exactly one worker, so they are exact; the
+// data element itself is Hogwild across workers (the reference's async server serialises
+// per message; DC-ASGD exists precisely to tolerate this kind of staleness).
+// ---------------------------------------------------------------------------
+struct PushStateDev {
+  int S;
+  void* shard[MVB_MAX_RANKS];
+  void* st0[MVB_MAX_RANKS];
+  void* st1[MVB_MAX_RANKS];
+  int64_t off[MVB_MAX_RANKS];
+  int64_t len[MVB_MAX_RANKS];
+  int64_t stride[MVB_MAX_RANKS];
+};
+
+template <int UPD, typename T>
+__global__ void __launch_bounds__(256)
+push_stateful_kernel(const T* __restrict__ delta, const __grid_constant__ PushStateDev p, MvbAddOpt opt, int me) {
+  using U = Updater<UPD, T>;
+  const int groups = p.S;
+  const int grp = blockIdx.x % groups;
+  const int s = (me + 1 + grp) % groups;
+  const int64_t gidx = blockIdx.x / groups;
+  const int64_t gcount = (gridDim.x - grp + groups - 1) / groups;
+  const int64_t tid = gidx * blockDim.x + threadIdx.x;
+  const int64_t stride = gcount * blockDim.x;
+  const T* src = delta + p.off[s];
+  T* data = (T*)p.shard[s];
+  const int64_t woff = U::kPerWorker ? (int64_t)opt.worker_id * p.stride[s] : 0;
+  T* s0p = (T*)p.st0[s] + woff;
+  T* s1p = (T*)p.st1[s] + woff;
+  const int64_t len = p.len[s];
+  for (int64_t i = tid; i < len; i += stride) {
+    const T d_old = data[i];
+    T d = d_old, s0 = (T)0, s1 = (T)0;
+    if constexpr (U::kStates >= 1) s0 = s0p[i];
+    if constexpr (U::kStates >= 2) s1 = s1p[i];
+    U::Apply(d, src[i], s0, s1, opt);
+    if constexpr (U::kStates >= 1) s0p[i] = s0;
+    if constexpr (U::kStates >= 2) s1p[i] = s1;
+    // the step is applied ATOMICALLY (no lost updates when several workers push at once); only
+    // the value DC-ASGD's compensation term saw may be stale, which is what it is built for
+    red_add(data + i, (T)(d - d_old));
+  }
+}
+
+template <typename T>
+int dispatch_push_stateful(int upd, const void* delta, const PushStateDev& p, const MvbAddOpt* opt, int me,
+                           int64_t total, cudaStream_t st) {
+  const int threads = 256;
+  int64_t blocks = (total + threads - 1) / threads;
+  int64_t cap = (int64_t)mvb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < p.S) blocks = p.S;
+  blocks = (blocks + p.S - 1) / p.S * p.S;
+#define MVB_PUSH_ST(U) push_stateful_kernel<U, T><<<(int)blocks, threads, 0, st>>>((const T*)delta, p, *opt, me)
+  switch (upd) {
+    case MVB_UPD_MOMENTUM: MVB_PUSH_ST(MVB_UPD_MOMENTUM); break;
+    case MVB_UPD_ADAGRAD: MVB_PUSH_ST(MVB_UPD_ADAGRAD); break;
+    case MVB_UPD_DCASGD: MVB_PUSH_ST(MVB_UPD_DCASGD); break;
+    case MVB_UPD_DCASGDA: MVB_PUSH_ST(MVB_UPD_DCASGDA); break;
+    default: return -2;
+  }
+#undef MVB_PUSH_ST
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
+
+extern "C" int mvb_push_dense_stateful(int dtype, int updater, const void* delta, int nservers,
+                                       void* const* shard_ptrs, void* const* state0_ptrs,
+                                       void* const* state1_ptrs, const int64_t* shard_offs,
+                                       const int64_t* shard_lens, const int64_t* state_strides,
+                                       const MvbAddOpt* opt, int me, void* stream) {
+  PushStateDev p{};
+  p.S = nservers;
+  int64_t total = 0;
+  for (int s = 0; s < nservers; ++s) {
+    p.shard[s] = shard_ptrs[s];
+    p.st0[s] = state0_ptrs ? state0_ptrs[s] : nullptr;
+    p.st1[s] = state1_ptrs ? state1_ptrs[s] : nullptr;
+    p.off[s] = shard_offs[s];
+    p.len[s] = shard_lens[s];
+    p.stride[s] = state_strides[s];
+    total += shard_lens[s];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case MVB_F32: return dispatch_push_stateful<float>(updater, delta, p, opt, me, total, st);
+    case MVB_F64: return dispatch_push_stateful<double>(updater, delta, p, opt, me, total, st);
+  }
+  return -1;
+}
 
 extern "C" int mvb_add_dense_fused(const MvbDenseAdd* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

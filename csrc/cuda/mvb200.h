@@ -137,6 +137,13 @@ int mvb_push_dense_red(int dtype, const void* delta, int nservers, void* const* 
                        const int64_t* shard_offs, const int64_t* shard_lens, float sign,
                        void* stream);
 
+/* One-sided async push for STATEFUL updaters: remote read-modify-write of the owners' shard +
+ * state slabs (state must be peer-mapped). Per-worker state is exact; data is Hogwild. */
+int mvb_push_dense_stateful(int dtype, int updater, const void* delta, int nservers,
+                            void* const* shard_ptrs, void* const* state0_ptrs, void* const* state1_ptrs,
+                            const int64_t* shard_offs, const int64_t* shard_lens,
+                            const int64_t* state_strides, const MvbAddOpt* opt, int me, void* stream);
+
 /* ---- row-sparse Get / Add (K3, K4, K10) ------------------------------------ */
 typedef struct MvbRowMap {
   int64_t num_row, num_col;

@@ -125,8 +125,11 @@ class DenseDeviceTable(_AsyncOps):
         self.n_states, self.state_per_worker = nst, per_worker
         self.state_stride = (self.my_len + 3) // 4 * 4
         slab = self.state_stride * (W if per_worker else 1)
-        self.state = [torch.zeros(max(slab, 1), dtype=self.dtype, device=rt.device)
-                      for _ in range(nst)]
+        # state slabs are symmetric (peer-mapped) too: the async one-sided push of a stateful
+        # updater updates the owner's state remotely
+        self._state_bufs = [rt.alloc_symm(max(slab, 1) * self.esz) for _ in range(nst)]
+        self.state = [b.tensor(self.dtype, max(slab, 1)) for b in self._state_bufs]
+        self.state_strides = [(l + 3) // 4 * 4 for l in self.lens]
         # collective path resources (lazy)
         self._stage: List = []
         self._stage_idx = 0
@@ -165,12 +168,12 @@ class DenseDeviceTable(_AsyncOps):
         return t.contiguous().view(-1)
 
     def _collective(self) -> bool:
-        stateless = self.updater in (N.UPD_DEFAULT, N.UPD_SGD)
-        if self.rt.size == 1:
+        """BSP (or one process): owner-side fused reduce-scatter + updater. Async: one-sided
+        pushes (red.add for stateless updaters, remote read-modify-write for stateful ones), so
+        workers need not call add() in lockstep -- the reference's async-server contract."""
+        if self.rt.size == 1 or self.sync:
             return True
-        if self.sync:
-            return True
-        return not (stateless and bool(FLAGS.get("async_one_sided")))
+        return not bool(FLAGS.get("async_one_sided"))
 
     # ------------------------------------------------------------------ Add (whole table)
     def add(self, delta=None, option: Optional[AddOption] = None, staged: bool = False) -> None:
@@ -203,13 +206,25 @@ class DenseDeviceTable(_AsyncOps):
                 self._launch_fused(ptrs, opts, pads=True, multicast=mc)
             else:
                 src = self._as_device(delta)
-                sign = -1.0 if self.updater == N.UPD_SGD else 1.0
                 sp = (C.c_void_p * self.S)(*self.shard_ptrs)
                 so = (C.c_int64 * self.S)(*self.offs)
                 sl = (C.c_int64 * self.S)(*self.lens)
-                N.check(lib.mvb_push_dense_red(self.dcode, C.c_void_p(src.data_ptr()), self.S, sp, so,
-                                               sl, C.c_float(sign), C.c_void_p(N.stream_ptr())),
-                        "mvb_push_dense_red")
+                if self.updater in (N.UPD_DEFAULT, N.UPD_SGD) or self.dtype in (torch.int32, torch.int64):
+                    sign = -1.0 if self.updater == N.UPD_SGD else 1.0
+                    N.check(lib.mvb_push_dense_red(self.dcode, C.c_void_p(src.data_ptr()), self.S, sp, so,
+                                                   sl, C.c_float(sign), C.c_void_p(N.stream_ptr())),
+                            "mvb_push_dense_red")
+                else:
+                    ranks = [rt.server_id_to_rank(s) for s in range(self.S)]
+                    s0 = (C.c_void_p * self.S)(*[self._state_bufs[0].ptrs[r] for r in ranks])
+                    s1 = (C.c_void_p * self.S)(*[(self._state_bufs[1].ptrs[r] if self.n_states > 1 else 0)
+                                                  for r in ranks])
+                    ss = (C.c_int64 * self.S)(*self.state_strides)
+                    ao = _opt_struct(opt)
+                    ao.worker_id = max(rt.worker_id(), 0)
+                    N.check(lib.mvb_push_dense_stateful(self.dcode, self.updater, C.c_void_p(src.data_ptr()),
+                                                        self.S, sp, s0, s1, so, sl, ss, C.byref(ao), rt.rank,
+                                                        C.c_void_p(N.stream_ptr())), "mvb_push_dense_stateful")
                 self._keep = src
         return self._record()
 
@@ -326,7 +341,7 @@ class DenseDeviceTable(_AsyncOps):
         return "wait"
 
     def free(self) -> None:
-        for b in [self.shard_buf] + list(self._stage):
+        for b in [self.shard_buf] + list(self._stage) + list(self._state_bufs):
             self.rt.release_symm(b)
         self._stage = []
         self.shard = None

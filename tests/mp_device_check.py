@@ -90,6 +90,17 @@ def scenario_async():
     ts.add(delta)
     mv.barrier()
     check("async_sgd_sign", torch.equal(ts.get(), -delta * W))
+    # stateful updater in ASYNC mode: one-sided, no lockstep -- ranks add a different number of
+    # times; per-worker AdaGrad history makes the result exact: each add of delta=lr moves by
+    # rho / sqrt(k) at the k-th add of that worker
+    ta = mv.ArrayTable(100003, "float32", updater="adagrad")
+    my_adds = 1 + r
+    for k in range(my_adds):
+        ta.add(torch.full((100003,), 0.01, device="cuda"), mv.AddOption(learning_rate=0.01, rho=0.1))
+    mv.barrier()
+    exp_a = -sum(0.1 / (k ** 0.5) for w in range(W) for k in range(1, 2 + w))
+    check("async_stateful_one_sided", torch.allclose(ta.get(), torch.full((100003,), exp_a, device="cuda"), rtol=1e-4),
+          f"{ta.get()[:3].tolist()} vs {exp_a}")
     # rows
     m = mv.MatrixTable(5000, 300, "float32")
     ids = torch.arange(r, 5000, 7, device="cuda")
