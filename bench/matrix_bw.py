@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--array-gb", type=float, default=0.0)
     ap.add_argument("--updater", default="sgd")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--no-replica", action="store_true", help="disable the fused Add->Get replica push")
     a = ap.parse_args()
     mv.init(sync=True)
     world, rank = mv.size(), mv.rank()
@@ -54,6 +55,9 @@ def main():
         n = a.rows * a.cols
         table = mv.MatrixTable(a.rows, a.cols, "float32", updater=a.updater)
         shape = f"MatrixTable {a.rows}x{a.cols} fp32 ({a.updater})"
+    if world > 1 and not a.no_replica:
+        table.enable_replica()
+        mv.barrier()
     nbytes = n * 4
     out = torch.empty(n, device="cuda")
     opt = mv.AddOption(momentum=0.9, learning_rate=0.01)
@@ -66,14 +70,23 @@ def main():
             table.wait(table.add_async(out, opt))
 
     res = {"shape": shape, "n_gpus": world, "bytes": nbytes}
+    res["replica"] = bool(world > 1 and not a.no_replica)
     res["ours_add_ms"] = timed(our_add, a.iters, world)
     res["ours_get_ms"] = timed(lambda: table.get(out), a.iters, world)
+    def add_get():
+        our_add()
+        table.get(out)
+    res["ours_add_plus_get_ms"] = timed(add_get, a.iters, world)
     if n % world == 0:
         from baseline.nccl_path import NcclDenseTable
         nt = NcclDenseTable(n, a.updater if a.updater in ("sgd", "momentum_sgd", "default") else "sgd")
         delta = torch.full((n,), 1e-3, device="cuda")
         res["nccl_add_ms"] = timed(lambda: nt.add(delta), a.iters, world)
         res["nccl_get_ms"] = timed(lambda: nt.get(out), a.iters, world)
+        def nccl_add_get():
+            nt.add(delta)
+            nt.get(out)
+        res["nccl_add_plus_get_ms"] = timed(nccl_add_get, a.iters, world)
         del delta
     link = 770.0   # GB/s per direction per GPU (measured peer copy, B200_PROFILING.md)
     hbm = 6571.9

@@ -27,6 +27,9 @@ struct DenseAddDev {
   uint32_t mask;
   const T* delta[MVB_MAX_RANKS];
   const T* delta_mc;     // NVLS multicast view of the staging buffers (or nullptr)
+  T* replica_mc;         // multicast view of every rank's table replica (fused Add -> Get push)
+  T* replica[MVB_MAX_RANKS];   // per-rank replica pointers (fallback without multicast)
+  int has_replica;
   MvbAddOpt opts[MVB_MAX_RANKS];
   float scale, clip;
   MvbPeers pads;
@@ -85,6 +88,25 @@ MVB_DEVINL void pk_store(T* p, const Pack<T, VEC>& r) {
   }
 }
 
+// Fused Add -> Get: the freshly updated tile is pushed into EVERY rank's table replica while it
+// is still in registers -- one multimem.st (the NVSwitch replicates it) or a store per peer --
+// so the BSP step's Get degenerates to a flag wait (no second pass over NVLink).
+template <typename T, int VEC, typename A>
+MVB_DEVINL void push_replica(const A& a, int64_t i, const Pack<T, VEC>& d) {
+  if constexpr (std::is_same<T, float>::value && VEC == 4) {
+    if (a.replica_mc != nullptr) {
+      multimem_st_v4_f32(a.replica_mc + a.shard_off + i, make_float4(d.v[0], d.v[1], d.v[2], d.v[3]));
+      return;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < MVB_MAX_RANKS; ++r)
+    if (r < a.world) {
+      if constexpr (VEC == 1) a.replica[r][a.shard_off + i] = d.v[0];
+      else st_na_v4(a.replica[r] + a.shard_off + i, *reinterpret_cast<const uint4*>(&d));
+    }
+}
+
 template <int UPD, typename T, int VEC>
 __global__ void __launch_bounds__(256)
 add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
@@ -129,6 +151,7 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
         U::Apply(d.v[2], prep_delta<T>(sum.z, a.scale, a.clip), z0, z1, a.opts[0]);
         U::Apply(d.v[3], prep_delta<T>(sum.w, a.scale, a.clip), z0, z1, a.opts[0]);
         pk_store<T, VEC>(a.shard + i, d);
+        if (a.has_replica) push_replica<T, VEC>(a, i, d);
         continue;
       }
     }
@@ -162,6 +185,7 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
     }
     if constexpr (U::kStates >= 1 && !U::kPerWorker) pk_store<T, VEC>(a.state0 + i, s0);
     pk_store<T, VEC>(a.shard + i, d);
+    if (a.has_replica) push_replica<T, VEC>(a, i, d);
   }
   // scalar tail (shard_len % VEC) handled by the first threads of block 0
   if (VEC > 1 && blockIdx.x == 0) {
@@ -184,6 +208,8 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
       }
       if constexpr (U::kStates >= 1 && !U::kPerWorker) a.state0[i] = s0;
       a.shard[i] = d;
+      if (a.has_replica)
+        for (int r = 0; r < a.world; ++r) a.replica[r][a.shard_off + i] = d;
     }
   }
 
@@ -232,6 +258,12 @@ int launch_add(const MvbDenseAdd* h, cudaStream_t st) {
     if (w < h->nworkers && !aligned16<T>(h->delta_ptrs[w])) vec_ok = false;
   }
   a.delta_mc = (const T*)h->delta_multicast;
+  a.has_replica = h->replica_ptrs[0] != nullptr || h->replica_multicast != nullptr;
+  a.replica_mc = (T*)h->replica_multicast;
+  for (int r = 0; r < MVB_MAX_RANKS; ++r) {
+    a.replica[r] = (T*)h->replica_ptrs[r];
+    if (a.has_replica && r < h->world && !aligned16<T>(h->replica_ptrs[r])) vec_ok = false;
+  }
   a.scale = h->scale;
   a.clip = h->clip;
   a.has_pads = h->pads != nullptr;

@@ -90,6 +90,9 @@ typedef struct MvbDenseAdd {
   const void* delta_multicast;  /* optional NVLS multicast mapping of the staging buffers:
                                    default/sgd fp32 adds then reduce in the switch */
   MvbAddOpt opts[MVB_MAX_RANKS];         /* per worker          */
+  /* fused Add -> Get (optional): push the updated shard into every rank's full-table replica */
+  void* replica_ptrs[MVB_MAX_RANKS];     /* indexed by rank, NULL = off */
+  void* replica_multicast;               /* NVLS multicast view of the replicas or NULL */
   float scale;            /* delta pre-scale (1 = none)  */
   float clip;             /* |delta| clip, 0 = off       */
   /* fused signalling (optional) */

@@ -48,7 +48,7 @@ class DenseAdd(C.Structure):
     _fields_ = [
         ("dtype", C.c_int), ("updater", C.c_int), ("shard", vp), ("state0", vp), ("state1", vp),
         ("shard_len", i64), ("shard_off", i64), ("state_stride", i64), ("nworkers", C.c_int),
-        ("worker_mask", C.c_uint32), ("delta_ptrs", VP8), ("delta_multicast", vp), ("opts", AddOptx8), ("scale", C.c_float),
+        ("worker_mask", C.c_uint32), ("delta_ptrs", VP8), ("delta_multicast", vp), ("opts", AddOptx8), ("replica_ptrs", VP8), ("replica_multicast", vp), ("scale", C.c_float),
         ("clip", C.c_float), ("pads", C.POINTER(vp)), ("me", C.c_int), ("world", C.c_int),
         ("ch_ready", C.c_int), ("ch_done", C.c_int), ("epoch", C.c_uint64), ("worker_rank", I32x8),
         ("is_worker", C.c_int), ("err_flag", vp), ("fin_flag", vp), ("done_counter", vp),

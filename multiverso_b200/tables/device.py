@@ -139,6 +139,8 @@ class DenseDeviceTable(_AsyncOps):
         self._done_counter = rt.done_counter_ptr()
         self._fin = torch.zeros(1, dtype=torch.int32, device=rt.device)
         self._finished = False
+        self._replica = None          # fused Add -> Get: full-table replica on every rank
+        self._replica_epoch = -1
         self.table_id = rt.register_table(self)
         rt.barrier()   # MV_CreateTable ends with a barrier (multiverso.h:35-41)
 
@@ -152,6 +154,16 @@ class DenseDeviceTable(_AsyncOps):
         b = self._stage[self._stage_idx]
         self._stage_idx ^= 1
         return b
+
+    def enable_replica(self) -> None:
+        """Fused Add -> Get for BSP whole-table traffic: every collective Add also pushes the
+        updated shard into a full-table replica on every rank (one NVLS ``multimem.st`` per tile,
+        or a store per peer), so the following ``get`` is a flag wait + local copy instead of a
+        second trip over NVLink. Valid for tables updated ONLY through whole-table Adds
+        (ArrayTable semantics); row Adds from other ranks do not reach the replicas.
+        Collective: call on every rank."""
+        if self._replica is None and self.rt.size > 1:
+            self._replica = self.rt.alloc_multicast(self.size * self.esz) or self.rt.alloc_symm(self.size * self.esz)
 
     def staging(self) -> torch.Tensor:
         """Zero-copy Add: write your delta into the returned full-size tensor, then call
@@ -247,6 +259,11 @@ class DenseDeviceTable(_AsyncOps):
             a.worker_rank[w] = rt.worker_id_to_rank(w) if rt.size > 1 else 0
         a.scale, a.clip = 1.0, 0.0
         a.delta_multicast = multicast or None
+        if pads and self._replica is not None:
+            for r in range(rt.size):
+                a.replica_ptrs[r] = self._replica.ptrs[r]
+            a.replica_multicast = getattr(self._replica, "multicast_ptr", 0) or None
+            self._replica_epoch = self.add_epoch + 1
         self._pads_arr = rt.pads_array() if pads else None
         a.pads = C.cast(self._pads_arr, C.POINTER(C.c_void_p)) if pads else None
         a.me, a.world = rt.rank, rt.size
@@ -272,6 +289,22 @@ class DenseDeviceTable(_AsyncOps):
 
     def _get_async(self, out):
         rt, lib = self.rt, N.cuda_lib()
+        if self._replica is not None and self._replica_epoch == self.add_epoch and self.add_epoch > 0:
+            # fused Add -> Get: the owners already pushed epoch `add_epoch` into our replica
+            mask = 0
+            for s_ in range(self.S):
+                mask |= 1 << rt.server_id_to_rank(s_)
+            with monitor("WORKER_TABLE_GET", cuda=True, nbytes=self.size * self.esz):
+                N.check(lib.mvb_wait(rt.pads_array(), rt.rank, rt.size, self.ch_done, C.c_uint64(self.add_epoch),
+                                     C.c_uint32(mask), C.c_void_p(rt.err_flag.data_ptr()),
+                                     C.c_double(float(FLAGS.get("barrier_timeout_s"))),
+                                     C.c_void_p(N.stream_ptr())), "mvb_wait")
+                rep = self._replica.tensor(self.dtype, self.size)
+                if out is None:
+                    out = rep.clone()
+                else:
+                    out.view(-1).copy_(rep)
+            return self._record(), out
         if out is None:
             out = torch.empty(self.size, dtype=self.dtype, device=rt.device)
         flat = out.view(-1)
@@ -341,7 +374,8 @@ class DenseDeviceTable(_AsyncOps):
         return "wait"
 
     def free(self) -> None:
-        for b in [self.shard_buf] + list(self._stage) + list(self._state_bufs):
+        for b in [self.shard_buf] + list(self._stage) + list(self._state_bufs) + \
+                ([self._replica] if self._replica is not None else []):
             self.rt.release_symm(b)
         self._stage = []
         self.shard = None
@@ -373,6 +407,10 @@ class ArrayDeviceTable(DenseDeviceTable):
 
     def __init__(self, size: int, dtype="float32", updater=None, init_value=None):
         super().__init__(int(size), 1, dtype, updater, init_value)
+        # whole-table ops only => the fused Add -> Get replica is always coherent in BSP mode
+        if self.sync and self.rt.size > 1 and bool(FLAGS.get("replicate_get")):
+            self.enable_replica()
+            self.rt.barrier()
 
 
 class MatrixDeviceTable(DenseDeviceTable):
