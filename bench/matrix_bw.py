@@ -43,7 +43,7 @@ def main():
     ap.add_argument("--array-gb", type=float, default=0.0)
     ap.add_argument("--updater", default="sgd")
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--no-replica", action="store_true", help="disable the fused Add->Get replica push")
+    ap.add_argument("--replica", action="store_true", help="enable the fused Add->Get replica push")
     a = ap.parse_args()
     mv.init(sync=True)
     world, rank = mv.size(), mv.rank()
@@ -55,7 +55,7 @@ def main():
         n = a.rows * a.cols
         table = mv.MatrixTable(a.rows, a.cols, "float32", updater=a.updater)
         shape = f"MatrixTable {a.rows}x{a.cols} fp32 ({a.updater})"
-    if world > 1 and not a.no_replica:
+    if world > 1 and a.replica:
         table.enable_replica()
         mv.barrier()
     nbytes = n * 4
@@ -70,7 +70,7 @@ def main():
             table.wait(table.add_async(out, opt))
 
     res = {"shape": shape, "n_gpus": world, "bytes": nbytes}
-    res["replica"] = bool(world > 1 and not a.no_replica)
+    res["replica"] = bool(world > 1 and a.replica)
     res["ours_add_ms"] = timed(our_add, a.iters, world)
     res["ours_get_ms"] = timed(lambda: table.get(out), a.iters, world)
     def add_get():
@@ -98,7 +98,7 @@ def main():
             res[k + "_frac_of_floor"] = res["floor_ms"] / res[k + "_ms"]
     if rank == 0:
         os.makedirs("gpurun_out", exist_ok=True)
-        tag = "array" if a.array_gb > 0 else "matrix"
+        tag = ("array" if a.array_gb > 0 else "matrix") + ("_replica" if a.replica else "")
         with open(f"gpurun_out/{tag}_bw_n{world}.json", "w") as f:
             json.dump(res, f, indent=1)
         print(json.dumps(res), flush=True)

@@ -28,7 +28,8 @@ _DEFAULTS: Dict[str, Any] = {
     "kv_capacity": 1 << 20,       # slots per KV shard
     "async_one_sided": True,      # async mode: stateless updaters push with red.add
     "nvls": True,                 # use NVSwitch multicast (multimem.*) for MV_Aggregate when available
-    "replicate_get": True,        # BSP ArrayTables: fused Add -> Get (updated shards pushed to replicas)
+    "replicate_get": False,       # BSP ArrayTables: fused Add -> Get (updated shards pushed to replicas);
+                                  # measured at 2 GPUs: multimem.st push costs +3.0 ms/GB, a net loss there
     "nvls_add": False,            # also reduce dense Adds in the switch (egress-bound either way;
                                   # measured slower than the P2P pull at 2 GPUs: 3.18 vs 1.71 ms)
 }

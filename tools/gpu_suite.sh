@@ -52,11 +52,19 @@ extra)
   timeout 300 $L bench/matrix_bw.py --array-gb 4 --updater momentum_sgd > gpurun_out/array_bw.log 2>&1; echo "array_bw rc=$?"; grep '^{' gpurun_out/array_bw.log | tail -1 | cut -c1-600
   timeout 300 $L bench/logreg_sparse.py > gpurun_out/logreg_sparse.log 2>&1; echo "logreg_sparse rc=$?"; grep '^{' gpurun_out/logreg_sparse.log | tail -1 | cut -c1-400
   ;;
+replica)
+  L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+7))"
+  timeout 300 $L bench/matrix_bw.py --replica > gpurun_out/matrix_bw_replica.log 2>&1; echo "matrix_bw replica rc=$?"; grep '^{' gpurun_out/matrix_bw_replica.log | tail -1 | cut -c1-700
+  ;;
 gemm)
   if [ "$NG" -gt 1 ]; then L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+6))"; else L="python"; fi
   timeout 300 $L bench/get_gemm.py > gpurun_out/get_gemm.log 2>&1; echo "get_gemm rc=$?"; grep '^\[' gpurun_out/get_gemm.log | tail -1 | cut -c1-900
   ;;
-ncu_gemm)
+ncu_replica)
+  L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+7))"
+  timeout 300 $L bench/matrix_bw.py --replica > gpurun_out/matrix_bw_replica.log 2>&1; echo "matrix_bw replica rc=$?"; grep '^{' gpurun_out/matrix_bw_replica.log | tail -1 | cut -c1-700
+  ;;
+gemm)
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:get_gemm_fused -s 2 -c 1 -f -o gpurun_out/get_gemm python bench/get_gemm.py --shapes 4096x65536x512 --iters 2 > gpurun_out/ncu_get_gemm.log 2>&1; echo "ncu_gemm rc=$?"
   ;;
 refarm)
