@@ -52,6 +52,9 @@ extra)
   timeout 300 $L bench/matrix_bw.py --array-gb 4 --updater momentum_sgd > gpurun_out/array_bw.log 2>&1; echo "array_bw rc=$?"; grep '^{' gpurun_out/array_bw.log | tail -1 | cut -c1-600
   timeout 300 $L bench/logreg_sparse.py > gpurun_out/logreg_sparse.log 2>&1; echo "logreg_sparse rc=$?"; grep '^{' gpurun_out/logreg_sparse.log | tail -1 | cut -c1-400
   ;;
+sanitize)
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitizer_memcheck.log python -m pytest tests/test_gpu_tables.py tests/test_gpu_get_gemm.py -q -m gpu -x -k "not 1048576 and not 1000-1000-512 and not 2048-300-300" > gpurun_out/sanitizer_memcheck.out 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY" gpurun_out/sanitizer_memcheck.log | tail -3; tail -2 gpurun_out/sanitizer_memcheck.out
+  ;;
 replica)
   L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+7))"
   timeout 300 $L bench/matrix_bw.py --replica > gpurun_out/matrix_bw_replica.log 2>&1; echo "matrix_bw replica rc=$?"; grep '^{' gpurun_out/matrix_bw_replica.log | tail -1 | cut -c1-700
@@ -60,7 +63,10 @@ gemm)
   if [ "$NG" -gt 1 ]; then L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+6))"; else L="python"; fi
   timeout 300 $L bench/get_gemm.py > gpurun_out/get_gemm.log 2>&1; echo "get_gemm rc=$?"; grep '^\[' gpurun_out/get_gemm.log | tail -1 | cut -c1-900
   ;;
-ncu_replica)
+ncu_sanitize)
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitizer_memcheck.log python -m pytest tests/test_gpu_tables.py tests/test_gpu_get_gemm.py -q -m gpu -x -k "not 1048576 and not 1000-1000-512 and not 2048-300-300" > gpurun_out/sanitizer_memcheck.out 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY" gpurun_out/sanitizer_memcheck.log | tail -3; tail -2 gpurun_out/sanitizer_memcheck.out
+  ;;
+replica)
   L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+7))"
   timeout 300 $L bench/matrix_bw.py --replica > gpurun_out/matrix_bw_replica.log 2>&1; echo "matrix_bw replica rc=$?"; grep '^{' gpurun_out/matrix_bw_replica.log | tail -1 | cut -c1-700
   ;;
