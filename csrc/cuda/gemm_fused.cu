@@ -5,32 +5,39 @@
 // W is a MatrixTable whose rows are range-sharded over the servers (peer-mapped HBM). The
 // reference pulls the table into a host buffer (MatrixWorkerTable::Get -> ProcessReplyGet
 // memcpy, src/table/matrix_table.cpp:58-76,316-341) and only then multiplies on the device.
-// Here the pulled row block never lands in local HBM: each CTA owns one 64-row tile of W
-// (one server's shard), streams it ONCE from the owner over NVLink with TMA
-// (cp.async.bulk.tensor, 128B swizzle) straight into shared memory, and feeds it as the B
-// operand of tcgen05.mma (kind::tf32, M=128, N=64, K=8) against up to 8 row tiles of the
-// local X -- 8 fp32 accumulators of 64 TMEM columns each = all 512 columns -- so the NVLink
-// traffic is |W| regardless of M while X tiles are re-read from local L2.
+// Here the pulled row block never lands in local HBM: a work item is one 128-row tile of W
+// (one server's shard) times up to 512 rows of X.  The W tile is streamed from its owner over
+// NVLink with TMA (cp.async.bulk.tensor, 128B swizzle) straight into shared memory and is the
+// *A* operand of tcgen05.mma (kind::tf32, M=128, N=256, K=8): the accumulator is the transposed
+// tile Y^T[w_row, x_row] -- 128 TMEM lanes x 2 x 256 columns = all of TMEM -- so W crosses NVLink
+// ceil(M/512) times while X (the B operand, N=256 per instruction: the shape the tensor pipe runs
+// at full rate) is re-read from local L2.  Lanes = consecutive Y columns, so the epilogue's
+// tcgen05.ld registers store straight to 128-byte coalesced row segments of Y.
 //
-//   warp 0      TMA producer: B ring (one W tile per k-block) + A ring (MT X tiles per k-block)
+//   warp 0      TMA producer: W ring (one tile per k-block) + X ring (<=2 chunks per k-block)
 //   warp 1      TMEM alloc + single-thread tcgen05.mma issue; tcgen05.commit frees smem slots
 //   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> global stores
+// Persistent CTAs (one per SM); the two 256-column accumulators are handed back to the MMA
+// issuer one by one, so the next item's MMAs overlap the rest of the epilogue (items with
+// M <= 256 alternate accumulators = full double buffering).
 #include <cuda.h>
+#include <algorithm>
 #include <cstdio>
 #include "mvb_common.cuh"
 
 namespace {
 
-constexpr int BM = 128;          // UMMA_M
-constexpr int BN = 64;           // UMMA_N: W rows per CTA
+constexpr int WM = 128;          // UMMA_M: W rows per tile (TMEM lanes)
+constexpr int XN = 256;          // UMMA_N: X rows per MMA (TMEM columns per accumulator)
+constexpr int XC_MAX = 2;        // accumulators (X chunks) per item: 2 * 256 = 512 TMEM columns
 constexpr int BK = 32;           // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int UK = 8;            // UMMA_K for tf32
-constexpr int MT_MAX = 8;        // X row tiles per CTA (8 * 64 = 512 TMEM columns)
-constexpr int A_STAGES = 6;      // 16 KB each
-constexpr int B_STAGES = 4;      // 8 KB each
-constexpr int A_BYTES = BM * BK * 4;
-constexpr int B_BYTES = BN * BK * 4;
-constexpr int kThreads = 192;
+constexpr int W_STAGES = 4;      // 16 KB each
+constexpr int X_STAGES = 4;      // 32 KB each
+constexpr int W_BYTES = WM * BK * 4;
+constexpr int X_BYTES = XN * BK * 4;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct GemmDev {
   float* y;
@@ -38,8 +45,9 @@ struct GemmDev {
   int64_t ldy;
   int S;
   int64_t row_begin[MVB_MAX_RANKS + 1];   // global row range of server s
-  int tile_begin[MVB_MAX_RANKS + 1];      // first n-tile index of server s
-  int mt_groups;                          // ceil(ceil(M/128) / MT_MAX)
+  int tile_begin[MVB_MAX_RANKS + 1];      // first W-tile index of server s
+  int tiles_n;                            // total W tiles
+  int x_groups;                           // ceil(M / 512)
 };
 
 MVB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,6 +56,9 @@ MVB_DEVINL void mbar_init(uint64_t* bar, int count) {
 }
 MVB_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+MVB_DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 MVB_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -71,8 +82,8 @@ MVB_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 // c=F32, a=b=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(XN >> 3) << 17) |
+                                ((uint32_t)(WM >> 4) << 24);
 
 MVB_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -84,11 +95,44 @@ MVB_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                ::"r"(smem_u32(bar)) : "memory");
 }
+MVB_DEVINL void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 
 struct SmemLayout {
-  uint64_t a_full[A_STAGES], a_empty[A_STAGES], b_full[B_STAGES], b_empty[B_STAGES], acc_full;
+  uint64_t w_full[W_STAGES], w_empty[W_STAGES], x_full[X_STAGES], x_empty[X_STAGES];
+  uint64_t acc_full[XC_MAX], acc_empty[XC_MAX];
   uint32_t tmem_base;
 };
+
+// One work item = (W tile, group of up to 512 X rows).  Items are dealt round-robin to the
+// persistent CTAs with the W tile varying fastest, so CTAs running side by side share the same X
+// rows in L2 while each streams its own W tile.
+struct Item {
+  int s, XC;
+  int64_t n_local, n_global, n_valid, x0;
+};
+MVB_DEVINL Item decode_item(const GemmDev& g, int item) {
+  Item it;
+  const int xg = item / g.tiles_n, ntile = item - xg * g.tiles_n;
+  int s = 0;
+  while (s + 1 < g.S && ntile >= g.tile_begin[s + 1]) ++s;
+  it.s = s;
+  it.n_local = (int64_t)(ntile - g.tile_begin[s]) * WM;       // row inside the shard
+  it.n_global = g.row_begin[s] + it.n_local;
+  it.n_valid = min((int64_t)WM, g.row_begin[s + 1] - it.n_global);
+  it.x0 = (int64_t)xg * (XN * XC_MAX);
+  it.XC = (int)min((int64_t)XC_MAX, (g.M - it.x0 + XN - 1) / XN);
+  return it;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
@@ -100,33 +144,21 @@ get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment: align the dynamic segment by hand
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* a_tiles = smem;                              // A_STAGES * 16 KB (1024-aligned)
-  unsigned char* b_tiles = smem + A_STAGES * A_BYTES;         // B_STAGES * 8 KB
-  SmemLayout* sl = reinterpret_cast<SmemLayout*>(b_tiles + B_STAGES * B_BYTES);
+  unsigned char* x_tiles = smem;                              // X_STAGES * 32 KB (1024-aligned)
+  unsigned char* w_tiles = smem + X_STAGES * X_BYTES;         // W_STAGES * 16 KB
+  SmemLayout* sl = reinterpret_cast<SmemLayout*>(w_tiles + W_STAGES * W_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- which W tile / which group of X row tiles ---------------------------------------
-  const int ntile = blockIdx.x;
-  int s = 0;
-  while (s + 1 < g.S && ntile >= g.tile_begin[s + 1]) ++s;
-  const int64_t n_local = (int64_t)(ntile - g.tile_begin[s]) * BN;       // row inside the shard
-  const int64_t n_global = g.row_begin[s] + n_local;
-  const int64_t n_valid = min((int64_t)BN, g.row_begin[s + 1] - n_global);
-  const int tiles_m = (int)((g.M + BM - 1) / BM);
-  const int mt0 = blockIdx.y * MT_MAX;
-  const int MT = min(MT_MAX, tiles_m - mt0);
+  const int num_items = g.tiles_n * g.x_groups;
   const int num_kb = (int)((g.K + BK - 1) / BK);
-  const CUtensorMap* map_w = s == 0 ? &map_w0 : s == 1 ? &map_w1 : s == 2 ? &map_w2 : s == 3 ? &map_w3
-                           : s == 4 ? &map_w4 : s == 5 ? &map_w5 : s == 6 ? &map_w6 : &map_w7;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&sl->a_full[i], 1); mbar_init(&sl->a_empty[i], 1); }
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&sl->b_full[i], 1); mbar_init(&sl->b_empty[i], 1); }
-    mbar_init(&sl->acc_full, 1);
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&sl->w_full[i], 1); mbar_init(&sl->w_empty[i], 1); }
+    for (int i = 0; i < X_STAGES; ++i) { mbar_init(&sl->x_full[i], 1); mbar_init(&sl->x_empty[i], 1); }
+    for (int i = 0; i < XC_MAX; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    // all 512 columns: MT accumulators of BN columns (power-of-two allocation)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sl->tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -138,78 +170,115 @@ get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
   if (warp == 0) {
     if (lane == 0) {
       // ============================== TMA PRODUCER ======================================
-      int ia = 0, ib = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&sl->b_empty[ib], pb ^ 1u);
-        mbar_expect_tx(&sl->b_full[ib], B_BYTES);
-        tma_load_2d(b_tiles + ib * B_BYTES, map_w, kb * BK, (int)n_local, &sl->b_full[ib]);   // peer HBM
-        if (++ib == B_STAGES) { ib = 0; pb ^= 1u; }
-        for (int mt = 0; mt < MT; ++mt) {
-          mbar_wait(&sl->a_empty[ia], pa ^ 1u);
-          mbar_expect_tx(&sl->a_full[ia], A_BYTES);
-          tma_load_2d(a_tiles + ia * A_BYTES, &map_x, kb * BK, (mt0 + mt) * BM, &sl->a_full[ia]);
-          if (++ia == A_STAGES) { ia = 0; pa ^= 1u; }
+      int iw = 0, ix = 0;
+      uint32_t pw = 0, px = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(g, item);
+        const int s = it.s;
+        const CUtensorMap* map_w = s == 0 ? &map_w0 : s == 1 ? &map_w1 : s == 2 ? &map_w2 : s == 3 ? &map_w3
+                                 : s == 4 ? &map_w4 : s == 5 ? &map_w5 : s == 6 ? &map_w6 : &map_w7;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&sl->w_empty[iw], pw ^ 1u);
+          mbar_expect_tx(&sl->w_full[iw], W_BYTES);
+          tma_load_2d(w_tiles + iw * W_BYTES, map_w, kb * BK, (int)it.n_local, &sl->w_full[iw]);   // peer HBM
+          if (++iw == W_STAGES) { iw = 0; pw ^= 1u; }
+          for (int xc = 0; xc < it.XC; ++xc) {
+            mbar_wait(&sl->x_empty[ix], px ^ 1u);
+            mbar_expect_tx(&sl->x_full[ix], X_BYTES);
+            tma_load_2d(x_tiles + ix * X_BYTES, &map_x, kb * BK, (int)(it.x0 + xc * XN), &sl->x_full[ix]);
+            if (++ix == X_STAGES) { ix = 0; px ^= 1u; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ============================== MMA ISSUER =========================================
-      int ia = 0, ib = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&sl->b_full[ib], pb);
-        const uint32_t b_addr = smem_u32(b_tiles + ib * B_BYTES);
-        for (int mt = 0; mt < MT; ++mt) {
-          mbar_wait(&sl->a_full[ia], pa);
-          asm volatile("tcgen05.fence::after_thread_sync;");
-          const uint32_t a_addr = smem_u32(a_tiles + ia * A_BYTES);
+      int iw = 0, ix = 0;
+      uint32_t pw = 0, px = 0;
+      uint32_t q = 0;                                 // running accumulator-chunk counter: slot = q & 1
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(g, item);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&sl->w_full[iw], pw);
+          const uint32_t w_addr = smem_u32(w_tiles + iw * W_BYTES);
+          for (int xc = 0; xc < it.XC; ++xc) {
+            const uint32_t qc = q + (uint32_t)xc, slot = qc & 1u;
+            // the slot must have been drained by the epilogue of its previous use
+            if (kb == 0 && qc >= 2) mbar_wait(&sl->acc_empty[slot], ((qc >> 1) - 1u) & 1u);
+            mbar_wait(&sl->x_full[ix], px);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t x_addr = smem_u32(x_tiles + ix * X_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            // advance 32 bytes inside the 128-byte swizzle row per UMMA_K step
-            umma_tf32(tmem_base + (uint32_t)(mt * BN), make_smem_desc(a_addr + k * UK * 4),
-                      make_smem_desc(b_addr + k * UK * 4), (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / UK; ++k) {
+              // advance 32 bytes inside the 128-byte swizzle row per UMMA_K step
+              umma_tf32(tmem_base + slot * XN, make_smem_desc(w_addr + k * UK * 4),
+                        make_smem_desc(x_addr + k * UK * 4), (kb | k) ? 1u : 0u);
+            }
+            umma_commit(&sl->x_empty[ix]);            // X slot is free once these MMAs retire
+            if (++ix == X_STAGES) { ix = 0; px ^= 1u; }
           }
-          umma_commit(&sl->a_empty[ia]);            // A slot is free once these MMAs retire
-          if (++ia == A_STAGES) { ia = 0; pa ^= 1u; }
+          umma_commit(&sl->w_empty[iw]);
+          if (++iw == W_STAGES) { iw = 0; pw ^= 1u; }
         }
-        umma_commit(&sl->b_empty[ib]);
-        if (++ib == B_STAGES) { ib = 0; pb ^= 1u; }
+        for (int xc = 0; xc < it.XC; ++xc) umma_commit(&sl->acc_full[(q + (uint32_t)xc) & 1u]);
+        q += (uint32_t)it.XC;
       }
-      umma_commit(&sl->acc_full);                   // every accumulator is final
     }
   } else {
     // ================================ EPILOGUE ===========================================
-    mbar_wait(&sl->acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;");
+    // lanes = consecutive W rows = consecutive Y columns: register j of the warp is one 128-byte
+    // segment of Y row (x0 + ... + j).
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
-    for (int mt = 0; mt < MT; ++mt) {
-      const int64_t m = (int64_t)(mt0 + mt) * BM + quarter * 32 + lane;
+    uint32_t q = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const Item it = decode_item(g, item);
+      const int64_t ncol = it.n_local + quarter * 32 + lane;                 // row inside the W tile's shard
+      const bool n_ok = quarter * 32 + lane < it.n_valid;
+      float* ycol = g.y + it.n_global + quarter * 32 + lane;
+      (void)ncol;
+      for (int xc = 0; xc < it.XC; ++xc, ++q) {
+        const uint32_t slot = q & 1u;
+        mbar_wait(&sl->acc_full[slot], (q >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int64_t m0 = it.x0 + (int64_t)xc * XN;
+        const int rows = (int)min((int64_t)XN, g.M - m0);
+#pragma unroll 1
+        for (int cc = 0; cc < XN; cc += 64) {
+          if (cc < rows) {
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * XN + (uint32_t)cc;
+            tmem_ld_32x32(taddr, v0);
+            tmem_ld_32x32(taddr + 32, v1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (cc + 64 >= rows || cc + 64 >= XN) {
+              // last TMEM read of this accumulator: hand the columns back before storing
+              asm volatile("tcgen05.fence::before_thread_sync;");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&sl->acc_empty[slot]);
+            }
+            if (n_ok) {
+              float* out = ycol + (m0 + cc) * g.ldy;
+              if (cc + 64 <= rows) {
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * BN + c0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < g.M) {
-          float* out = g.y + m * g.ldy + n_global + c0;
+                for (int j = 0; j < 32; ++j) out[(int64_t)j * g.ldy] = __uint_as_float(v0[j]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < n_valid) out[j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j) out[(int64_t)(32 + j) * g.ldy] = __uint_as_float(v1[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (cc + j < rows) out[(int64_t)j * g.ldy] = __uint_as_float(v0[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (cc + 32 + j < rows) out[(int64_t)(32 + j) * g.ldy] = __uint_as_float(v1[j]);
+              }
+            }
+          }
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -263,7 +332,7 @@ extern "C" int mvb_get_gemm_fused(const MvbGetGemm* h, void* stream) {
   GemmDev g{};
   g.y = h->y; g.M = h->M; g.N = h->N; g.K = h->K; g.ldy = h->N; g.S = wm.nservers;
   CUtensorMap maps[1 + MVB_MAX_RANKS];
-  int rc = make_map(&maps[0], h->x, h->M, h->K, h->K, BM);
+  int rc = make_map(&maps[0], h->x, h->M, h->K, h->K, XN);
   if (rc) return rc;
   int tiles = 0;
   for (int s = 0; s < wm.nservers; ++s) {
@@ -274,17 +343,18 @@ extern "C" int mvb_get_gemm_fused(const MvbGetGemm* h, void* stream) {
     g.row_begin[s] = lo;
     g.row_begin[s + 1] = hi;
     g.tile_begin[s] = tiles;
-    tiles += (int)((hi - lo + BN - 1) / BN);
+    tiles += (int)((hi - lo + WM - 1) / WM);
     g.tile_begin[s + 1] = tiles;
-    rc = make_map(&maps[1 + s], wm.shard_ptrs[s], hi - lo > 0 ? hi - lo : 1, h->K, h->K, BN);
+    rc = make_map(&maps[1 + s], wm.shard_ptrs[s], hi - lo > 0 ? hi - lo : 1, h->K, h->K, WM);
     if (rc) return rc;
   }
   for (int s = wm.nservers; s < MVB_MAX_RANKS; ++s) maps[1 + s] = maps[1];
-  const int tiles_m = (int)((h->M + BM - 1) / BM);
-  g.mt_groups = (tiles_m + MT_MAX - 1) / MT_MAX;
-  const size_t smem = A_STAGES * A_BYTES + B_STAGES * B_BYTES + sizeof(SmemLayout) + 1024;
+  g.x_groups = (int)((h->M + XN * XC_MAX - 1) / (XN * XC_MAX));
+  g.tiles_n = tiles;
+  const size_t smem = X_STAGES * X_BYTES + W_STAGES * W_BYTES + sizeof(SmemLayout) + 1024;
   MVB_CUDA_CHECK(cudaFuncSetAttribute(get_gemm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)tiles, (unsigned)g.mt_groups);
+  const int64_t items = (int64_t)tiles * g.x_groups;
+  dim3 grid((unsigned)std::min<int64_t>(items, mvb_num_sms()));
   get_gemm_fused_kernel<<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
                                                       maps[7], maps[8], g);
   MVB_CUDA_CHECK(cudaGetLastError());

@@ -63,14 +63,7 @@ gemm)
   if [ "$NG" -gt 1 ]; then L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+6))"; else L="python"; fi
   timeout 300 $L bench/get_gemm.py > gpurun_out/get_gemm.log 2>&1; echo "get_gemm rc=$?"; grep '^\[' gpurun_out/get_gemm.log | tail -1 | cut -c1-900
   ;;
-ncu_sanitize)
-  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitizer_memcheck.log python -m pytest tests/test_gpu_tables.py tests/test_gpu_get_gemm.py -q -m gpu -x -k "not 1048576 and not 1000-1000-512 and not 2048-300-300" > gpurun_out/sanitizer_memcheck.out 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY" gpurun_out/sanitizer_memcheck.log | tail -3; tail -2 gpurun_out/sanitizer_memcheck.out
-  ;;
-replica)
-  L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+7))"
-  timeout 300 $L bench/matrix_bw.py --replica > gpurun_out/matrix_bw_replica.log 2>&1; echo "matrix_bw replica rc=$?"; grep '^{' gpurun_out/matrix_bw_replica.log | tail -1 | cut -c1-700
-  ;;
-gemm)
+ncu_gemm)
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:get_gemm_fused -s 2 -c 1 -f -o gpurun_out/get_gemm python bench/get_gemm.py --shapes 4096x65536x512 --iters 2 > gpurun_out/ncu_get_gemm.log 2>&1; echo "ncu_gemm rc=$?"
   ;;
 refarm)
