@@ -51,14 +51,21 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int = 0):
-        self.rows = []
+        self.rows = []          # (monotonic time of receipt, csv line)
         self.proc = None
         self.gpu = gpu_index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.monotonic()
+
+    def mark_end(self):
+        self.t_end = time.monotonic()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -67,7 +74,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -78,7 +85,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows
+                if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.25)]
+        if not rows:                                   # timed region shorter than one sampling period
+            rows = [r for (_, r) in self.rows[-2:]]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -148,20 +159,25 @@ def main():
         we.train_block(dev_blocks[i], compute_loss=True)
 
     # ------------------------------------------------------------ device-timed arm
+    # the clock sampler (one looping nvidia-smi) is started BEFORE the warm-up so that its start-up
+    # (driver enumeration, which can stall kernel launches for milliseconds) is not inside the timed
+    # region; only the rows received during the timed region are used, and it is killed after.
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
     for i in range(W):
         step_device(i)
     sync_all()
     mv.Dashboard.reset()
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()
     launches0 = we.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     ev0.record()
     for i in range(K):
         step_device(W + i)
     ev1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     ms_local = ev0.elapsed_time(ev1)
     launches = we.kernel_launches - launches0
     sync_all()

@@ -49,6 +49,8 @@ def main():
         y = torch.empty(M, Nr, device="cuda")
         wbuf = torch.empty(Nr * K, device="cuda")
         fused = timed(lambda: get_gemm(t, x, y), a.iters, world)
+        from multiverso_b200 import _native
+        cfg = int(_native.cuda_lib().mvb_get_gemm_last_config())
         def unfused():
             t.get(wbuf)
             torch.matmul(x, wbuf.view(Nr, K).t(), out=y)
@@ -59,7 +61,8 @@ def main():
         link_floor = (wbytes * (world - 1) / world / 770e9 * 1e3) if world > 1 else (wbytes / 6571.9e9 * 1e3)
         out.append({"M": M, "N": Nr, "K": K, "fused_ms": fused, "unfused_get_plus_cublas_ms": unf, "get_only_ms": get_only,
                     "fused_tflops": flops / fused / 1e9, "w_bytes": wbytes, "w_stream_floor_ms": link_floor,
-                    "speedup_vs_unfused": unf / fused})
+                    "speedup_vs_unfused": unf / fused,
+                    "ctas_per_mma": cfg // 1000, "grid": cfg % 1000})
         t.free()
         del x, y, wbuf
     if rank == 0:

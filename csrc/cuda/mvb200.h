@@ -303,12 +303,14 @@ int mvb_regularize(float* grad, const float* w, int64_t len, int type, float coe
 typedef struct MvbGetGemm {
   const float* x;            /* [M x K] fp32 row-major, local     */
   float* y;                  /* [M x N] fp32                      */
-  float* w_cache;            /* optional [N x K] local copy       */
+  float* w_cache;            /* reserved (must be NULL)           */
   int64_t M, N, K;
   MvbRowMap wmap;            /* N rows x K cols over servers      */
+  int local_server;          /* index of the shard in local HBM, -1 if none */
 } MvbGetGemm;
 int mvb_get_gemm_fused(const MvbGetGemm* g, void* stream);
 int mvb_get_gemm_supported(void);
+int mvb_get_gemm_last_config(void);  /* ctas*1000 + grid of the last launch */
 
 #ifdef __cplusplus
 }

@@ -112,7 +112,7 @@ class LrDense(C.Structure):
 
 class GetGemm(C.Structure):
     _fields_ = [("x", vp), ("y", vp), ("w_cache", vp), ("M", i64), ("N", i64), ("K", i64),
-                ("wmap", RowMap)]
+                ("wmap", RowMap), ("local_server", C.c_int)]
 
 
 class NativeError(RuntimeError):

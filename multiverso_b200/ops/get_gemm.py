@@ -37,5 +37,6 @@ def get_gemm(table, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     g.wmap.rows_per_server = table.rps
     for s in range(table.S):
         g.wmap.shard_ptrs[s] = table.shard_ptrs[s]
+    g.local_server = table.sid if table.S > 1 else 0
     N.check(N.cuda_lib().mvb_get_gemm_fused(C.byref(g), C.c_void_p(N.stream_ptr())), "mvb_get_gemm_fused")
     return out

@@ -149,6 +149,19 @@ def scenario_async():
     ref = xg.double() @ Wfull.double().T
     check("get_gemm_peer_tma", (yg.double() - ref).abs().max().item() < 4e-3 * 16 * 4, str((yg.double() - ref).abs().max().item()))
     mv.barrier()
+    # several x-groups over remote shards: the first pass stages each W tile in the local scratch
+    # (TMA store), the later passes load from it -- ragged M, shard sizes that are not tile multiples
+    wt2 = mv.MatrixTable(3001, 320, "float32", min_value=-1.0, max_value=1.0, seed=4)
+    mv.barrier()
+    W2 = wt2.get().view(3001, 320).clone()
+    for Mrows in (700, 1500):
+        x2 = torch.randn(Mrows, 320, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+        y2 = get_gemm(wt2, x2)
+        torch.cuda.synchronize()
+        ref2 = x2.double() @ W2.double().T
+        err2 = (y2.double() - ref2).abs().max().item()
+        check(f"get_gemm_peer_scratch_M{Mrows}", err2 < 4e-3 * 18 * 4, str(err2))
+    mv.barrier()
     # distributed WordEmbedding block (block mode)
     from multiverso_b200.models.wordembedding import WordEmbedding, WordEmbeddingOption, synthetic_zipf_corpus
     we = WordEmbedding(WordEmbeddingOption(embeding_size=300, init_learning_rate=0.01), 200000)

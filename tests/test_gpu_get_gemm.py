@@ -6,7 +6,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("M,Nrows,K", [(128, 64, 32), (256, 128, 64), (1000, 1000, 512), (77, 10, 784), (2048, 300, 300)])
+@pytest.mark.parametrize("M,Nrows,K", [(128, 64, 32), (256, 128, 64), (1000, 1000, 512), (77, 10, 784), (2048, 300, 300), (1300, 700, 1024)])
 def test_get_gemm_matches_fp32_reference(mv_device, M, Nrows, K):
     from multiverso_b200.ops import get_gemm, get_gemm_supported
     mv = mv_device
