@@ -35,7 +35,7 @@ def timed(fn, iters, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--shapes", default="4096x65536x512,1024x1000000x512,8192x16384x1024")
+    ap.add_argument("--shapes", default="4096x65536x512,1024x1000000x512,512x1000000x512,8192x16384x1024")
     ap.add_argument("--iters", type=int, default=10)
     a = ap.parse_args()
     mv.init()

@@ -183,13 +183,13 @@ struct SmemLayout {
   uint32_t tmem_base;
 };
 
-// Schedule: worker w (a CTA, or a CTA pair) owns W tiles w, w + workers, ... and runs ALL x-groups
-// of a tile back to back, x-group fastest.  CTAs running side by side work on the same X rows (L2
-// hits) while each streams its own W tile, and a worker meets its W tile again right away:
+// Schedule: the (W tile, x-group) units, x-group fastest, are cut into one contiguous, balanced range
+// per worker (a CTA, or a CTA pair): a worker runs the x-groups of a tile back to back (X, a few MB,
+// stays in L2 for everybody) and meets its W tile again right away:
 //  * local shard: the second read is an L2 hit instead of a second HBM pass;
-//  * remote shard (peer lines are never cached in the local L2): during the first x-group every
+//  * remote shard (peer lines are never cached in the local L2): during the tile's first unit every
 //    W stage that the MMAs have consumed is written to a per-CTA scratch tile in local memory with
-//    a TMA store, and the later x-groups load from the scratch (which stays L2-resident: 128 rows x K
+//    a TMA store, and the later units load from the scratch (which stays L2-resident: 128 rows x K
 //    per CTA) -- W crosses NVLink exactly once whatever M is.
 struct Tile {
   int s;
@@ -236,6 +236,9 @@ get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
   const int worker = blockIdx.x / NC, num_workers = gridDim.x / NC;
 
   const int num_kb = (int)((g.K + BK - 1) / BK);
+  // contiguous, balanced range of (tile, x-group) units, x-group fastest
+  const int64_t units = (int64_t)g.tiles_n * g.x_groups;
+  const int64_t u_begin = units * worker / num_workers, u_end = units * (worker + 1) / num_workers;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(&sl->w_full[i], 1); mbar_init(&sl->w_empty[i], 1); }
@@ -271,23 +274,31 @@ get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
       int w_store[W_STAGES];
 #pragma unroll
       for (int i = 0; i < W_STAGES; ++i) w_store[i] = -1;
-      for (int ntile = worker; ntile < g.tiles_n; ntile += num_workers) {
-        const Tile t = decode_tile<NC>(g, ntile, (int)cta_rank);
-        const int s = t.s;
-        const CUtensorMap* map_w = s == 0 ? &map_w0 : s == 1 ? &map_w1 : s == 2 ? &map_w2 : s == 3 ? &map_w3
-                                 : s == 4 ? &map_w4 : s == 5 ? &map_w5 : s == 6 ? &map_w6 : &map_w7;
-        const bool cached = g.cache_on && s != g.local_s;
-        for (int xg = 0; xg < g.x_groups; ++xg) {
+      Tile t{};
+      const CUtensorMap* map_w = &map_w0;
+      bool cached = false;
+      for (int64_t u = u_begin; u < u_end; ++u) {
+        const int ntile = (int)(u / g.x_groups), xg = (int)(u - (int64_t)ntile * g.x_groups);
+        const bool first = (u == u_begin) || xg == 0;       // first unit of this tile on this worker
+        if (first) {
+          t = decode_tile<NC>(g, ntile, (int)cta_rank);
+          const int s = t.s;
+          map_w = s == 0 ? &map_w0 : s == 1 ? &map_w1 : s == 2 ? &map_w2 : s == 3 ? &map_w3
+                : s == 4 ? &map_w4 : s == 5 ? &map_w5 : s == 6 ? &map_w6 : &map_w7;
+          // worth staging only if this worker meets the tile again
+          cached = g.cache_on && s != g.local_s && (u + 1 < u_end) && (xg + 1 < g.x_groups);
+        }
+        {
           const int XC = chunks_of_group(g, xg);
           const int64_t x0 = (int64_t)xg * (XN * g.xc_item);
-          const bool from_scratch = cached && xg > 0;
+          const bool from_scratch = cached && !first;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait_prof(&sl->w_empty[iw], pw ^ 1u, a_we);
             // the previous content of this slot has been consumed by the MMAs: save it if it was a
             // first-pass stage of a remote tile (the smem read must finish before the slot is refilled)
             int pending = -1;
 #pragma unroll
-            for (int i = 0; i < W_STAGES; ++i) if (i == iw) { pending = w_store[i]; w_store[i] = (cached && xg == 0) ? kb : -1; }
+            for (int i = 0; i < W_STAGES; ++i) if (i == iw) { pending = w_store[i]; w_store[i] = (cached && first) ? kb : -1; }
             if (pending >= 0) {
               tma_store_2d(&map_c, pending * BK, c_row, w_tiles + iw * W_BYTES);
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -324,9 +335,8 @@ get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
       unsigned long long* a_wf = g.prof ? &c_wf : nullptr, * a_xf = g.prof ? &c_xf : nullptr,
                         * a_ae = g.prof ? &c_ae : nullptr;
       const long long t_start = clock64();
-      for (int ntile = worker; ntile < g.tiles_n; ntile += num_workers)
-      for (int xg = 0; xg < g.x_groups; ++xg) {
-        const int XC = chunks_of_group(g, xg);
+      for (int64_t u = u_begin; u < u_end; ++u) {
+        const int XC = chunks_of_group(g, (int)(u % g.x_groups));
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_prof(&sl->w_full[iw], pw, a_wf);
           const uint32_t w_addr = smem_u32(w_tiles + iw * W_BYTES);
@@ -366,11 +376,12 @@ get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
     unsigned long long c_af = 0;
     unsigned long long* a_af = (g.prof && warp == 2 && lane == 0 && leader) ? &c_af : nullptr;
     const long long t_start = clock64();
-    for (int ntile = worker; ntile < g.tiles_n; ntile += num_workers) {
+    for (int64_t u = u_begin; u < u_end; ++u) {
+     const int ntile = (int)(u / g.x_groups), xg = (int)(u - (int64_t)ntile * g.x_groups);
      const Tile t = decode_tile<NC>(g, ntile, (int)cta_rank);
      const bool n_ok = quarter * 32 + lane < t.n_valid;
      float* ycol = g.y + t.n_global + quarter * 32 + lane;
-     for (int xg = 0; xg < g.x_groups; ++xg) {
+     {
       const int XC = chunks_of_group(g, xg);
       const int64_t x0 = (int64_t)xg * (XN * g.xc_item);
       for (int xc = 0; xc < XC; ++xc, ++q) {
@@ -530,7 +541,7 @@ int launch_get_gemm(const MvbGetGemm* h, cudaStream_t st, int max_workers_overri
     max_workers = std::min(max_workers, nclusters);
   }
   if (max_workers_override > 0) max_workers = std::min(max_workers, max_workers_override);
-  const unsigned workers = (unsigned)std::min<int64_t>(tiles, max_workers);
+  const unsigned workers = (unsigned)std::min<int64_t>((int64_t)tiles * g.x_groups, max_workers);
   cfg.gridDim = dim3(workers * NC);
   // scratch for remote W tiles: one [128 x K] tile per CTA, grown on demand, reused by every call
   // (calls are expected on one stream; the buffer is only live inside a launch)

@@ -1,8 +1,11 @@
 """Fused Get + GEMM (K2-fused): ``y = x @ W^T`` where W is a row-sharded MatrixTable.
 
-The pulled row block is never materialised: the kernel streams each W tile once from its
-owner (local or peer HBM over NVLink) with TMA into shared memory and multiplies it with
-tcgen05.mma (TF32 operands, fp32 accumulation in TMEM) against the local activations.
+The pulled row block is never materialised: a persistent, warp-specialised kernel streams each
+W tile from its owner (local or peer HBM over NVLink) with TMA into shared memory and multiplies
+it with tcgen05.mma (CTA pairs, cta_group::2, TF32 operands, fp32 accumulation in TMEM) against
+the local activations; remote tiles are staged once in an L2-resident scratch, so W crosses NVLink
+once whatever M is.  Knobs (env): MVB_GEMM_CTAS=1 single-CTA MMAs, MVB_GEMM_XC=1|2 accumulators per
+work item, MVB_GEMM_WCACHE=0 no scratch staging, MVB_GEMM_PROF=1 in-kernel wait-cycle counters.
 Reference analogue: MatrixWorkerTable::Get followed by the application's first GEMM
 (e.g. LogReg Objective::Predict, Applications/LogisticRegression/src/objective/objective.cpp:113-120).
 """
