@@ -40,21 +40,35 @@ def parse_args():
     ap.add_argument("--negative", type=int, default=5)
     ap.add_argument("--window", type=int, default=5)
     ap.add_argument("--no-table-bw", action="store_true", help="skip the MatrixTable Get/Add sweep")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="world > 1: train / pull / push strictly one after the other (-is_pipeline 0)")
     return ap.parse_args()
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+
+    Started before the warm-up, stopped after the timed region; only samples taken inside the timed
+    region are reported.  Source: NVML in-process (``pynvml``, the library nvidia-smi itself uses: SM
+    clock, max SM clock, clocks-event reasons) every 200 ms, falling back to the recipe's looping
+    ``nvidia-smi --query-gpu=... -lms 200`` when pynvml is missing.  Polling is kept sparse on purpose:
+    on 2 GPUs a 50 ms poll / the nvidia-smi loop coincided with device-timed steps of 27-38 ms against
+    22-24 ms unpolled (same binary, same box; `profiles/README.md`).  BENCH_CLOCK_SAMPLER=smi|nvml|none."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index: int = 0):
-        self.rows = []          # (monotonic time of receipt, csv line)
+    def __init__(self, gpu_index: int = 0, source: str = "smi"):
+        self.rows = []          # (monotonic time, sm_mhz, sm_max_mhz, set(reasons))
         self.proc = None
+        self.thread = None
         self.gpu = gpu_index
+        self.source = os.environ.get("BENCH_CLOCK_SAMPLER", source)
         self.t_begin = self.t_end = None
+        self._stop = threading.Event()
 
     def mark_begin(self):
         self.t_begin = time.monotonic()
@@ -63,48 +77,84 @@ class ClockSampler:
         self.t_end = time.monotonic()
 
     def start(self):
+        if self.source == "none":
+            return
+        if self.source == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                try:
+                    import torch
+                    uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+                except Exception:
+                    h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+                self._nvml, self._h = pynvml, h
+                self.thread = threading.Thread(target=self._pump_nvml, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.source = "smi"
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread = threading.Thread(target=self._pump_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.monotonic(), line.strip()))
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _pump_nvml(self):
+        nv, h = self._nvml, self._h
         try:
-            self.proc.wait(timeout=5)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        rows = [r for (t, r) in self.rows
-                if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.25)]
-        if not rows:                                   # timed region shorter than one sampling period
-            rows = [r for (_, r) in self.rows[-2:]]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+            mx = None
+        fields = os.environ.get("BENCH_NVML_FIELDS", "both")
+        period = float(os.environ.get("BENCH_CLOCK_PERIOD", "0.2"))
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)) if fields in ("both", "clock") else 0.0
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if fields in ("both", "reasons") else 0
+                self.rows.append((time.monotonic(), sm, mx, {k for k, b in self.BITS.items() if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(period)
+
+    def _pump_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                sm, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+            reasons = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                "sw_power_cap"), f[5:9]) if v.lower().startswith("active")}
+            self.rows.append((time.monotonic(), sm, mx, reasons))
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"], "source": self.source}
+        rows = [r for r in self.rows
+                if self.t_begin is None or (self.t_begin <= r[0] <= (self.t_end or r[0]) + 0.25)]
+        if not rows:                                   # timed region shorter than one sampling period
+            rows = self.rows[-2:]
+        sm = sorted(r[1] for r in rows)
+        mx = [r[2] for r in rows if r[2] is not None]
+        reasons = set().union(*[r[3] for r in rows]) if rows else set()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def run_reference(args) -> None:
@@ -147,22 +197,28 @@ def main():
     dev_blocks = pinned.to(dev)               # device-timed arm: tokens already resident
     words_per_block = int((corpus[:B] >= 0).sum())
     tok_dev = torch.empty(B, dtype=torch.int32, device=dev)
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def sync_all():
         torch.cuda.synchronize()
         mv.barrier()
         torch.cuda.synchronize()
 
+    # world > 1: the reference's default pipeline (-is_pipeline 1): block i+1's PrepareData +
+    # RequestParameter overlap block i's training, block i's AddDeltaParameter overlaps block i+1's.
+    # Every step still issues exactly one prepare+pull, one train and one add-delta.
+    pipelined = world > 1 and not args.no_pipeline
+    blocks_list = [dev_blocks[i] for i in range(n_blocks)]        # stable tensor objects
+
     def step_device(i):
         we.learning_rate = opt.init_learning_rate * max(1e-4, 1.0 - i / (2.0 * n_blocks))
-        we.train_block(dev_blocks[i], compute_loss=True)
+        we.train_block(blocks_list[i], compute_loss=True,
+                       next_tokens=blocks_list[(i + 1) % n_blocks] if pipelined else None)
 
     # ------------------------------------------------------------ device-timed arm
     # the clock sampler (one looping nvidia-smi) is started BEFORE the warm-up so that its start-up
     # (driver enumeration, which can stall kernel launches for milliseconds) is not inside the timed
     # region; only the rows received during the timed region are used, and it is killed after.
-    sampler = ClockSampler(torch.cuda.current_device())
+    sampler = ClockSampler(torch.cuda.current_device(), source="nvml")
     if rank == 0:
         sampler.start()
     for i in range(W):
@@ -187,16 +243,41 @@ def main():
     loss_per_pair = float(we.loss.item()) / max(pairs, 1)
 
     # ------------------------------------------------------------ end-to-end arm
+    # Through the public API, every step: one H2D copy of a block of inputs from pinned host memory and
+    # one D2H read of the step's loss into pinned host memory, consumed on the host.  Both are
+    # software-pipelined the way a training loop does it: the loss of step i is read (event wait +
+    # float()) while step i+1 runs, and in pipelined mode the block copied during step i is step i+1's.
     we2_steps = K
+    we.flush()
     sync_all()
+    we._prefetched = None
+    tok2 = [tok_dev, torch.empty_like(tok_dev)]
+    loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    losses_host = []
+    if pipelined:
+        tok2[0].copy_(pinned[W], non_blocking=True)              # block 0 of the arm; each step copies the NEXT one
+        sync_all()
     t0 = time.perf_counter()
     for i in range(we2_steps):
-        tok_dev.copy_(pinned[W + i], non_blocking=True)          # H2D of this step's inputs
         we.loss.zero_()
-        we.train_block(tok_dev, compute_loss=True)
-        loss_host.copy_(we.loss, non_blocking=False)             # D2H of the step's result
+        if pipelined:
+            nxt = tok2[(i + 1) % 2]
+            nxt.copy_(pinned[W + (i + 1) % K], non_blocking=True)    # H2D of one block of inputs per step
+            we.train_block(tok2[i % 2], compute_loss=True, next_tokens=nxt)
+        else:
+            tok_dev.copy_(pinned[W + i], non_blocking=True)      # H2D of this step's inputs
+            we.train_block(tok_dev, compute_loss=True)
+        loss_pin[i % 2].copy_(we.loss, non_blocking=True)        # D2H of the step's result
+        loss_ev[i % 2].record()
+        if i > 0:                                                # consume step i-1's loss on the host
+            loss_ev[(i - 1) % 2].synchronize()
+            losses_host.append(float(loss_pin[(i - 1) % 2]))
+    loss_ev[(we2_steps - 1) % 2].synchronize()
+    losses_host.append(float(loss_pin[(we2_steps - 1) % 2]))
     torch.cuda.synchronize()
     e2e_s_local = time.perf_counter() - t0
+    assert len(losses_host) == we2_steps and all(l == l for l in losses_host)
     sync_all()
 
     # ------------------------------------------------------------ reduce over ranks (max time)
@@ -219,13 +300,15 @@ def main():
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": "ours",
             "config": {"model": CONFIG_MODEL, "global_batch": B * world, "seq_len": 1000,
-                       "parallelism": f"dp{world} row-sharded PS tables" if world > 1 else "1 GPU (worker+server)",
+                       "parallelism": (f"dp{world} row-sharded PS tables" + (", pipelined pull/push (-is_pipeline 1)" if pipelined else "")) if world > 1 else "1 GPU (worker+server)",
                        "block_words_per_gpu": B, "l2": "tables 2.4 GB >> 126 MB L2; new token block every step",
                        "pairs_per_word": pairs / max(1, words_per_block * (K + W)),
                        "loss_per_pair": loss_per_pair},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "words/s", "h2d_bytes_per_step": B * 4,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / K},
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / K,
+                    "note": "H2D of a block and D2H of the loss every step; loss of step i consumed on the host "
+                            "during step i+1" + ("; the block copied in step i is step i+1's" if pipelined else "")},
             "gpu_launches": launches,
             "extra": dict(extra, monitors_device_arm=monitors),
         }

@@ -150,15 +150,25 @@ def run(argv: List[str]) -> dict:
     dev = torch.device("cuda", torch.cuda.current_device())
     tok_dev = [torch.empty(block_tokens, dtype=torch.int32, device=dev) for _ in range(2)]
     words_done, blocks, last_log = 0, 0, time.time()
-    while True:
-        item = loader.q.get()
-        if item is None:
-            break
+    pipelined = bool(opt.is_pipeline) and size > 1
+
+    def stage(item, slot):
         toks, words, ep = item
-        buf = tok_dev[blocks & 1][: toks.numel()]
-        buf.copy_(toks, non_blocking=True)                  # -is_pipeline: next block's H2D overlaps training
+        buf = tok_dev[slot][: toks.numel()]
+        buf.copy_(toks, non_blocking=True)                  # H2D of block i+1 overlaps training of block i
+        return buf, words, ep
+
+    item = loader.q.get()
+    cur = stage(item, 0) if item is not None else None
+    while cur is not None:
+        item = loader.q.get()
+        nxt = stage(item, (blocks + 1) & 1) if item is not None else None
+        buf, words, ep = cur
         we.update_learning_rate()
-        we.train_block(buf, compute_loss=(blocks % 50 == 0))
+        # -is_pipeline (default on, util.cpp:25): the next block's parameters are requested while
+        # this one trains (distributed_wordembedding.cpp:199-222)
+        we.train_block(buf, compute_loss=(blocks % 50 == 0),
+                       next_tokens=nxt[0] if (pipelined and nxt is not None) else None)
         we.add_word_count(words * 1)                        # AddDeltaWordCount -> KV table
         words_done += words
         blocks += 1
@@ -169,6 +179,8 @@ def run(argv: List[str]) -> dict:
                 Log.info("Epoch %d  Words/sec %.0fk  lr %.6f  progress %.2f%%", ep, words_done / el / 1e3,
                          we.learning_rate, 100.0 * we.word_count_actual / max(1, opt.total_words * opt.epoch))
                 last_log = time.time()
+        cur = nxt
+    we.flush()
     torch.cuda.synchronize()
     mv.barrier()
     elapsed = time.time() - t0

@@ -48,7 +48,7 @@ class WordEmbeddingOption:
     cbow: bool = False
     stopwords: bool = False
     use_adagrad: bool = False
-    is_pipeline: bool = False
+    is_pipeline: bool = True        # util.cpp:25 (reference default)
     sample: float = 0.0
     data_block_size: int = 1 << 20
     embeding_size: int = 100
@@ -132,7 +132,11 @@ class WordEmbedding:
         self.word_count_actual = 0
         self.learning_rate = float(option.init_learning_rate)
         self._step = 0
-        self._map_in = self._map_out = None
+        self._maps = [None, None]       # two (map_in, map_out) sets: block i trains while i+1 is prepared
+        self._map_slot = 0
+        self._side = None               # side stream of the pipelined mode
+        self._prefetched = None
+        self._pending_side = False
         self.kernel_launches = 0
         self.kernel_variant = 0     # 0 auto | 1,2,3,5 register kernel (negatives in flight) | 10 TMA pipeline
 
@@ -175,9 +179,16 @@ class WordEmbedding:
         self.kernel_launches += 1
 
     # ------------------------------------------------------------------ one data block
-    def train_block(self, tokens: torch.Tensor, compute_loss: bool = True) -> None:
+    def train_block(self, tokens: torch.Tensor, compute_loss: bool = True,
+                    next_tokens: Optional[torch.Tensor] = None) -> None:
         """Train on one block of token ids (int32 CUDA tensor, negative = sentence break).
-        Asynchronous on the current stream; read ``loss`` / ``pairs`` after a sync."""
+        Asynchronous on the current stream; read ``loss`` / ``pairs`` after a sync.
+
+        ``next_tokens`` (world > 1, ``-is_pipeline``): the following block.  Its PrepareData +
+        RequestParameter run on a side stream while this block trains, and this block's
+        AddDeltaParameter runs there while the next one trains -- the reference's pipeline
+        (distributed_wordembedding.cpp:199-222: an extra thread prefetches the next block's
+        parameters during TrainIteration), with streams instead of an OpenMP thread."""
         assert tokens.is_cuda and tokens.dtype == torch.int32
         if self.rt.size == 1:
             with monitor("WE_TRAIN_BLOCK", cuda=True):
@@ -186,10 +197,58 @@ class WordEmbedding:
                              None if self.g2_out is None else self.g2_out.shard, self.D,
                              compute_loss=compute_loss)
             return
-        self._train_block_distributed(tokens, compute_loss)
+        if next_tokens is None and self._prefetched is None:
+            st = self._prepare_block(tokens, wait=True)
+            self._train_prepared(tokens, st, compute_loss)
+            self._add_delta(st)
+            return
+        # ---- pipelined ------------------------------------------------------------------
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        side = self._side
+        st = self._prefetched
+        self._prefetched = None
+        if st is None or st["tokens"] is not tokens:
+            st = self._prepare_block(tokens, wait=False)          # first block: nothing to overlap with
+            self._record_streams(st, side)                        # allocated here, last used over there
+        else:
+            main.wait_event(st["ready"])
+            self._record_streams(st, main)
+        inputs_ready = torch.cuda.Event()
+        inputs_ready.record(main)                                 # next_tokens (e.g. an H2D copy) is complete here
+        self._train_prepared(tokens, st, compute_loss)
+        trained = torch.cuda.Event()
+        trained.record(main)
+        with torch.cuda.stream(side):
+            if next_tokens is not None:
+                side.wait_event(inputs_ready)
+                nxt = self._prepare_block(next_tokens, wait=False)
+                nxt["tokens"] = next_tokens
+                nxt["ready"] = torch.cuda.Event()
+                nxt["ready"].record(side)
+                self._prefetched = nxt
+            side.wait_event(trained)
+            self._add_delta(st)
+        self._pending_side = True
 
-    def _train_block_distributed(self, tokens: torch.Tensor, compute_loss: bool) -> None:
-        o, dev, V, D = self.opt, self.dev, self.V, self.D
+    @staticmethod
+    def _record_streams(st: dict, stream) -> None:
+        for v in st.values():
+            if isinstance(v, torch.Tensor):
+                v.record_stream(stream)
+
+    def flush(self) -> None:
+        """Make the current stream wait for the pipelined AddDeltaParameter work."""
+        if self._side is not None and self._pending_side:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._pending_side = False
+
+    def _prepare_block(self, tokens: torch.Tensor, wait: bool) -> dict:
+        """PrepareData (data_block / communicator.cpp:117-155) + RequestParameter on the current stream."""
+        o, dev, V = self.opt, self.dev, self.V
+        slot = self._map_slot
+        self._map_slot ^= 1
         with monitor("WE_PREPARE_DATA", cuda=True):
             valid = tokens[tokens >= 0].to(torch.int64)
             in_ids = torch.unique(valid)
@@ -208,39 +267,49 @@ class WordEmbedding:
                 pool = torch.where(u < self.alias_prob[idx], idx, self.alias_idx[idx].to(torch.int64))
                 neg_pool = pool.to(torch.int32)
                 out_ids = torch.unique(torch.cat([in_ids, pool]))
-            if self._map_in is None:
-                self._map_in = torch.full((V,), -1, dtype=torch.int32, device=dev)
-                self._map_out = torch.full((V,), -1, dtype=torch.int32, device=dev)
-            self._map_in[in_ids] = torch.arange(in_ids.numel(), dtype=torch.int32, device=dev)
-            self._map_out[out_ids] = torch.arange(out_ids.numel(), dtype=torch.int32, device=dev)
+            if self._maps[slot] is None:
+                self._maps[slot] = (torch.full((V,), -1, dtype=torch.int32, device=dev),
+                                    torch.full((V,), -1, dtype=torch.int32, device=dev))
+            map_in, map_out = self._maps[slot]            # two sets: the next block is prepared while this one trains
+            map_in[in_ids] = torch.arange(in_ids.numel(), dtype=torch.int32, device=dev)
+            map_out[out_ids] = torch.arange(out_ids.numel(), dtype=torch.int32, device=dev)
         # RequestParameter (communicator.cpp:117-155): pull the block's rows
-        cache_in = self.input_table.get_rows(in_ids)
-        cache_out = self.output_table.get_rows(out_ids)
+        get = (lambda t, ids: t.get_rows(ids)) if wait else (lambda t, ids: t.get_rows_async(ids)[1])
+        cache_in = get(self.input_table, in_ids)
+        cache_out = get(self.output_table, out_ids)
         self.kernel_launches += 2
-        old_in, old_out = cache_in.clone(), cache_out.clone()
-        g2i = g2o = None
+        st = dict(in_ids=in_ids, out_ids=out_ids, neg_pool=neg_pool, map_in=map_in, map_out=map_out,
+                  cache_in=cache_in, cache_out=cache_out, old_in=cache_in.clone(), old_out=cache_out.clone(),
+                  g2i=None, g2o=None)
         if o.use_adagrad:
-            g2i = self.g2_in.get_rows(in_ids)
-            g2o = self.g2_out.get_rows(out_ids)
-            old_g2i, old_g2o = g2i.clone(), g2o.clone()
+            st["g2i"] = get(self.g2_in, in_ids)
+            st["g2o"] = get(self.g2_out, out_ids)
+            st["old_g2i"], st["old_g2o"] = st["g2i"].clone(), st["g2o"].clone()
+        return st
+
+    def _train_prepared(self, tokens: torch.Tensor, st: dict, compute_loss: bool) -> None:
         with monitor("WE_TRAIN_BLOCK", cuda=True):
-            self._launch(tokens, cache_in, cache_out, g2i, g2o, D, self._map_in, self._map_out,
-                         neg_pool, compute_loss)
+            self._launch(tokens, st["cache_in"], st["cache_out"], st["g2i"], st["g2o"], self.D,
+                         st["map_in"], st["map_out"], st["neg_pool"], compute_loss)
+
+    def _add_delta(self, st: dict) -> None:
         # AddDeltaParameter (communicator.cpp:206-249): delta = (trained - pulled) / W
+        o, D = self.opt, self.D
         inv = 1.0 / self.W
+        in_ids, out_ids = st["in_ids"], st["out_ids"]
         if D % 4 == 0:
-            self.input_table.add_rows_delta(in_ids, cache_in, old_in, inv)
-            self.output_table.add_rows_delta(out_ids, cache_out, old_out, inv)
+            self.input_table.add_rows_delta(in_ids, st["cache_in"], st["old_in"], inv)
+            self.output_table.add_rows_delta(out_ids, st["cache_out"], st["old_out"], inv)
             if o.use_adagrad:
-                self.g2_in.add_rows_delta(in_ids, g2i, old_g2i, inv)
-                self.g2_out.add_rows_delta(out_ids, g2o, old_g2o, inv)
+                self.g2_in.add_rows_delta(in_ids, st["g2i"], st["old_g2i"], inv)
+                self.g2_out.add_rows_delta(out_ids, st["g2o"], st["old_g2o"], inv)
             self.kernel_launches += 2
         else:
-            self.input_table.add_rows(in_ids, (cache_in - old_in) * inv)
-            self.output_table.add_rows(out_ids, (cache_out - old_out) * inv)
+            self.input_table.add_rows(in_ids, (st["cache_in"] - st["old_in"]) * inv)
+            self.output_table.add_rows(out_ids, (st["cache_out"] - st["old_out"]) * inv)
             if o.use_adagrad:
-                self.g2_in.add_rows(in_ids, (g2i - old_g2i) * inv)
-                self.g2_out.add_rows(out_ids, (g2o - old_g2o) * inv)
+                self.g2_in.add_rows(in_ids, (st["g2i"] - st["old_g2i"]) * inv)
+                self.g2_out.add_rows(out_ids, (st["g2o"] - st["old_g2o"]) * inv)
 
     # ------------------------------------------------------------------ word count (KV)
     def add_word_count(self, n: int) -> None:
@@ -253,10 +322,12 @@ class WordEmbedding:
     # ------------------------------------------------------------------ results
     def embeddings(self) -> torch.Tensor:
         """Whole input-embedding matrix [V, D] (SaveEmbedding pulls it in 100k-row batches)."""
+        self.flush()
         return self.input_table.get().view(self.V, self.D)
 
     def save_embedding(self, path: str, words=None, binary: bool = False) -> None:
         """word2vec text / binary format (distributed_wordembedding.cpp:263-325); rank 0 only."""
+        self.flush()
         if self.rt.rank != 0:
             return
         batch = 100000

@@ -174,6 +174,20 @@ def scenario_async():
         losses.append(float(we.loss.item()) / max(int(we.pairs.item()), 1))
     mv.barrier()
     check("wordembedding_block_mode", losses[-1] < losses[0] and all(l == l for l in losses), str(losses))
+    # pipelined block mode (-is_pipeline): block i+1 is prepared / pulled on a side stream while block i
+    # trains; block i's deltas are pushed while block i+1 trains
+    blocks = [torch.from_numpy(synthetic_zipf_corpus(200000, 200000, 1000, seed=10 * r + b)).cuda() for b in range(3)]
+    pl = []
+    for it in range(6):
+        we.loss.zero_(); we.pairs.zero_()
+        we.train_block(blocks[it % 3], next_tokens=blocks[(it + 1) % 3] if it < 5 else None)
+        torch.cuda.synchronize()
+        pl.append(float(we.loss.item()) / max(int(we.pairs.item()), 1))
+    we.flush()
+    torch.cuda.synchronize()
+    mv.barrier()
+    emb = we.embeddings()
+    check("wordembedding_pipelined", pl[-1] < pl[0] and all(l == l for l in pl) and bool(torch.isfinite(emb).all()), str(pl))
     mv.shutdown()
 
 
