@@ -231,6 +231,7 @@ def main():
     ev0.record()
     for i in range(K):
         step_device(W + i)
+    we.flush()                      # pipelined mode: the last block's AddDeltaParameter is part of the K steps
     ev1.record()
     torch.cuda.synchronize()
     sampler.mark_end()
@@ -258,7 +259,10 @@ def main():
     if pipelined:
         tok2[0].copy_(pinned[W], non_blocking=True)              # block 0 of the arm; each step copies the NEXT one
         sync_all()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(we2_steps + 1)]
+    host_t = []
     t0 = time.perf_counter()
+    step_ev[0].record()
     for i in range(we2_steps):
         we.loss.zero_()
         if pipelined:
@@ -270,6 +274,8 @@ def main():
             we.train_block(tok_dev, compute_loss=True)
         loss_pin[i % 2].copy_(we.loss, non_blocking=True)        # D2H of the step's result
         loss_ev[i % 2].record()
+        step_ev[i + 1].record()
+        host_t.append(time.perf_counter() - t0)
         if i > 0:                                                # consume step i-1's loss on the host
             loss_ev[(i - 1) % 2].synchronize()
             losses_host.append(float(loss_pin[(i - 1) % 2]))
@@ -278,6 +284,9 @@ def main():
     torch.cuda.synchronize()
     e2e_s_local = time.perf_counter() - t0
     assert len(losses_host) == we2_steps and all(l == l for l in losses_host)
+    e2e_trace = {"gpu_step_ms": [round(step_ev[i].elapsed_time(step_ev[i + 1]), 2) for i in range(we2_steps)],
+                 "host_enqueue_done_ms": [round(t * 1e3, 2) for t in host_t],
+                 "total_ms": round(e2e_s_local * 1e3, 2)}
     sync_all()
 
     # ------------------------------------------------------------ reduce over ranks (max time)
@@ -310,7 +319,7 @@ def main():
                     "note": "H2D of a block and D2H of the loss every step; loss of step i consumed on the host "
                             "during step i+1" + ("; the block copied in step i is step i+1's" if pipelined else "")},
             "gpu_launches": launches,
-            "extra": dict(extra, monitors_device_arm=monitors),
+            "extra": dict(extra, monitors_device_arm=monitors, e2e_trace_rank0=e2e_trace),
         }
         print(json.dumps(out), flush=True)
     mv.shutdown()
