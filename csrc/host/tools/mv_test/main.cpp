@@ -363,6 +363,65 @@ static void TestMatrix(bool sparse_wire) {   // Test/test_matrix_table.cpp:9-99
   delete s;
 }
 
+// Test/test_matrix_perf.cpp:32-171 (TestDensePerf / TestSparsePerf; "perf" tier of SURVEY section 4):
+// Get all rows -> every worker Adds its share of the first (p+1)/10 of the rows -> Get all rows,
+// timed and verified.  The reference hard-codes 1,000,000 x 50 and 10 turns per percentage; the
+// row count is an argument here (default 100,000, one turn) so the scenario can run in CI.
+static void TestMatrixPerf(bool sparse, int num_row) {
+  MV_Init();
+  const int C = 50, W = MV_NumWorkers(), me = MV_WorkerId();
+  const size_t size = static_cast<size_t>(num_row) * C;
+  std::vector<float> data(size), delta(size);
+  for (size_t i = 0; i < size; ++i) delta[i] = static_cast<float>(i % 100003);
+  Timer timer;
+  for (int percent = 0; percent < 10; ++percent) {
+    MatrixWorkerTable<float>* t;
+    if (sparse) {
+      MatrixOption<float> o;
+      o.num_row = num_row; o.num_col = C; o.is_sparse = true;
+      t = static_cast<MatrixWorkerTable<float>*>(MV_CreateTable(o));
+    } else {
+      t = MV_CreateTable(MatrixTableOption<float>(num_row, C));
+    }
+    if (!t) continue;                       // server-only rank
+    MV_Barrier();
+    GetOption gopt;
+    gopt.set_worker_id(me);
+    timer.Start();
+    t->Get(data.data(), size, &gopt);
+    const double first_ms = timer.elapse();
+    MV_Barrier();
+    std::vector<integer_t> ids;
+    std::vector<float*> ptrs;
+    for (int i = 0; i < num_row; ++i)
+      if (i % 10 <= percent && i % W == me) { ids.push_back(i); ptrs.push_back(delta.data() + static_cast<size_t>(i) * C); }
+    AddOption aopt;
+    aopt.set_worker_id(me);
+    timer.Start();
+    if (!ids.empty()) t->Add(ids, ptrs, C, &aopt);
+    const double add_ms = timer.elapse();
+    MV_Barrier();
+    timer.Start();
+    t->Get(data.data(), size, &gopt);
+    const double get_ms = timer.elapse();
+    bool ok = true;
+    for (int i = 0; i < num_row && ok; ++i)
+      for (int c = 0; c < C; ++c) {
+        const float expect = (i % 10 <= percent) ? delta[static_cast<size_t>(i) * C + c] : 0.f;
+        if (data[static_cast<size_t>(i) * C + c] != expect) { ok = false; break; }
+      }
+    EXPECT(ok);
+    if (me == 0)
+      printf("  %s %d x %d, add %d0%% of the rows: first get %.1f ms, add %.1f ms (%zu rows), get %.1f ms (%.2f GB/s)\n",
+             sparse ? "sparse" : "dense", num_row, C, percent + 1, first_ms, add_ms, ids.size(), get_ms,
+             size * sizeof(float) / get_ms / 1e6);
+    MV_Barrier();
+    delete t;
+  }
+  if (me == 0) Dashboard::Display();
+  MV_ShutDown();
+}
+
 static void TestNet() {   // Test/test_net.cpp:9-90
   NetInterface* net = NetInterface::Get();
   net->Init(nullptr, nullptr);
@@ -491,7 +550,7 @@ static void TestAppTables() {   // LogReg SparseTable / FTRLTable (sparse_table.
 
 int main(int argc, char* argv[]) {
   if (argc < 2) {
-    fprintf(stderr, "usage: mv_test unit|kv|array|array_async|net|matrix|sparse|allreduce|updater:<name> [-flag=value ...]\n");
+    fprintf(stderr, "usage: mv_test unit|kv|array|array_async|net|matrix|sparse|allreduce|apptables|dense_perf [rows]|sparse_perf [rows]|updater:<name> [-flag=value ...]\n");
     return 2;
   }
   std::string which = argv[1];
@@ -505,6 +564,8 @@ int main(int argc, char* argv[]) {
   else if (which == "sparse") TestMatrix(true);
   else if (which == "allreduce") TestAllreduce();
   else if (which == "apptables") TestAppTables();
+  else if (which == "dense_perf" || which == "sparse_perf")
+    TestMatrixPerf(which == "sparse_perf", argc > 2 ? atoi(argv[2]) : 100000);
   else if (which.rfind("updater:", 0) == 0) TestUpdatersAndCheckpoint(which.substr(8));
   else { fprintf(stderr, "unknown test %s\n", which.c_str()); return 2; }
   printf("[mv_test %s] %s\n", which.c_str(), g_fail ? "FAIL" : "PASS");

@@ -51,6 +51,13 @@ def test_native_updaters_and_checkpoint(updater):
     assert run_mp(2, BIN, f"updater:{updater}").count("PASS") == 2
 
 
+@pytest.mark.parametrize("scenario", ["dense_perf", "sparse_perf"])
+def test_matrix_perf_scenarios(scenario):
+    # Test/test_matrix_perf.cpp (reference "perf" tier), small row count: values verified, timings printed
+    out = run_mp(3, BIN, scenario, "6000")
+    assert out.count("PASS") == 3 and "add 100% of the rows" in out
+
+
 def test_backup_worker_ratio_flag():
     # with 4 workers and 25% backup workers the BSP quorum is 3: the scenario still completes
     out = run_mp(4, BIN, "array", "-backup_worker_ratio=25")
