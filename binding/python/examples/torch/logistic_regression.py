@@ -44,12 +44,14 @@ def main(epochs=5, batch=500, lr=0.13):
             w.requires_grad_(False); bb.requires_grad_(False)
             sync_all_mv_shared_vars()                      # push delta, pull merged parameters
         mv.barrier()
+        acc = None
         if mv.is_master_worker():
             with torch.no_grad():
                 acc = ((xva @ Wt.get_value() + b.get_value()).argmax(1) == yva).float().mean().item()
             print(f"epoch {epoch}: validation accuracy {acc:.4f}")
+    master = mv.is_master_worker()
     mv.shutdown()
-    return acc if mv.is_master_worker() else None
+    return acc if master else None
 
 
 if __name__ == "__main__":

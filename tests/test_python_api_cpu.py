@@ -118,3 +118,17 @@ def test_compat_binding_suite_single_and_multi_process():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", "2", "--", sys.executable, suite],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("example,args", [
+    ("logistic_regression.py", []),
+    ("resnet_cifar10.py", ["--epochs", "1", "--n", "1", "--samples", "256"]),
+    ("addition_rnn.py", ["--iters", "1", "--samples", "1500", "--digits", "2"]),
+])
+def test_binding_examples_two_workers(example, args):
+    """The binding examples (reference: binding/python/examples/theano/*) run with 2 workers on the host backend."""
+    script = os.path.join(ROOT, "binding", "python", "examples", "torch", example)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", "2", "--timeout", "280", "--",
+                        sys.executable, script, *args], capture_output=True, text=True, timeout=320, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
