@@ -198,6 +198,75 @@ allreduce_nvls_kernel(const __grid_constant__ ArDev<float> a, float* __restrict_
   handshake_end(a);
 }
 
+// Latency path (<= 1 MB): ONE launch does stage-in, handshake and reduction.  The staging buffer is
+// double-buffered by epoch parity, so no trailing "done" handshake is needed: a peer signals
+// ready(e) only after its call e-1 has completed, and every rank waited for all ready(e-1) during
+// its own call e-1 -- hence nobody can still be reading slot (e & 1) from epoch e-2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+allreduce_fused_kernel(const __grid_constant__ ArDev<T> a, const T* __restrict__ src, int64_t slot_off) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t nvec = a.n / VEC;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  T* mine = a.bufs[a.me] + slot_off;
+  const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+  if (aligned) {
+    for (int64_t v = v0; v < nvec; v += stride) st_v4(mine + v * VEC, ld_v4(src + v * VEC));
+    if (blockIdx.x == 0)
+      for (int64_t i = nvec * VEC + threadIdx.x; i < a.n; i += blockDim.x) mine[i] = src[i];
+  } else {
+    for (int64_t i = v0; i < a.n; i += stride) mine[i] = src[i];
+  }
+  __shared__ int is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned int prev = atomicAdd(a.done_counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+    if (is_last) *a.done_counter = 0;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < a.world) {
+    fence_sys();
+    uint64_t* slot = reinterpret_cast<uint64_t*>(a.pads.p[threadIdx.x]) + a.ch * MVB_MAX_RANKS + a.me;
+    st_release_sys_u64(slot, a.epoch);
+  }
+  if (threadIdx.x < a.world) {
+    const uint64_t* slot = reinterpret_cast<const uint64_t*>(a.pads.p[a.me]) + a.ch * MVB_MAX_RANKS + threadIdx.x;
+    if (!spin_wait_ge(slot, a.epoch, a.budget) && a.err) atomicExch(a.err, 6200 + threadIdx.x);
+  }
+  __syncthreads();
+  if (aligned) {
+    for (int64_t v = v0; v < nvec; v += stride) {
+      Pk<T, VEC> g[MVB_MAX_RANKS];
+#pragma unroll
+      for (int r = 0; r < MVB_MAX_RANKS; ++r)
+        if (r < a.world) {
+          uint4 u = ld_v4(a.bufs[r] + slot_off + v * VEC);
+          g[r] = *reinterpret_cast<Pk<T, VEC>*>(&u);
+        }
+      Pk<T, VEC> s = g[0];
+#pragma unroll
+      for (int r = 1; r < MVB_MAX_RANKS; ++r)
+        if (r < a.world) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) s.v[e] = (T)(s.v[e] + g[r].v[e]);
+        }
+      st_v4(a.out + v * VEC, *reinterpret_cast<uint4*>(&s));
+    }
+  }
+  const int64_t tail0 = aligned ? nvec * VEC : 0;
+  if (!aligned || blockIdx.x == 0) {
+    const int64_t i0 = aligned ? tail0 + threadIdx.x : v0, step = aligned ? blockDim.x : stride;
+    for (int64_t i = i0; i < a.n; i += step) {
+      T s = a.bufs[0][slot_off + i];
+      for (int r = 1; r < a.world; ++r) s = (T)(s + a.bufs[r][slot_off + i]);
+      a.out[i] = s;
+    }
+  }
+}
+
 template <typename T>
 ArDev<T> to_dev(const MvbAllreduce* h) {
   ArDev<T> a{};
@@ -241,6 +310,18 @@ int run(const MvbAllreduce* h, bool twoshot, cudaStream_t st) {
   return 0;
 }
 
+template <typename T>
+int run_fused(const MvbAllreduce* h, const void* src, int64_t slot_off_bytes, cudaStream_t st) {
+  ArDev<T> a = to_dev<T>(h);
+  constexpr int VEC = 16 / sizeof(T);
+  int64_t blocks = (h->n / VEC + 255) / 256;
+  if (blocks > 64) blocks = 64;                  // all CTAs must be co-resident (in-kernel grid handshake)
+  if (blocks < 1) blocks = 1;
+  allreduce_fused_kernel<T><<<(int)blocks, 256, 0, st>>>(a, (const T*)src, slot_off_bytes / (int64_t)sizeof(T));
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int dispatch(const MvbAllreduce* h, bool twoshot, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (h->world < 1 || h->world > MVB_MAX_RANKS) return -3;
@@ -273,6 +354,19 @@ extern "C" int mvb_allreduce_nvls(const MvbAllreduce* h, void* multicast_ptr, vo
   allreduce_twoshot_finish<float><<<(int)b2, 256, 0, st>>>(a);
   MVB_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mvb_allreduce_fused(const MvbAllreduce* h, const void* src, int64_t slot_off_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->world < 1 || h->world > MVB_MAX_RANKS || (slot_off_bytes & 15)) return -3;
+  switch (h->dtype) {
+    case MVB_F32: return run_fused<float>(h, src, slot_off_bytes, st);
+    case MVB_F64: return run_fused<double>(h, src, slot_off_bytes, st);
+    case MVB_I32: return run_fused<int>(h, src, slot_off_bytes, st);
+    case MVB_I64: return run_fused<long long>(h, src, slot_off_bytes, st);
+    case MVB_I8: return run_fused<signed char>(h, src, slot_off_bytes, st);
+  }
+  return -1;
 }
 
 extern "C" int mvb_allreduce_oneshot(const MvbAllreduce* a, void* stream) {

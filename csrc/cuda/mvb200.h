@@ -211,6 +211,9 @@ typedef struct MvbAllreduce {
 } MvbAllreduce;
 int mvb_allreduce_oneshot(const MvbAllreduce* a, void* stream);
 int mvb_allreduce_twoshot(const MvbAllreduce* a, void* stream);
+/* latency path: stage-in from `src`, handshake on channel a->ch (ready only) and one-shot reduction in
+ * ONE launch; bufs[r] + slot_off_bytes is the epoch's half of a double-buffered staging area */
+int mvb_allreduce_fused(const MvbAllreduce* a, const void* src, int64_t slot_off_bytes, void* stream);
 /* NVLS: in-switch reduction through the multicast mapping of the staging buffers (fp32) */
 int mvb_allreduce_nvls(const MvbAllreduce* a, void* multicast_ptr, void* stream);
 

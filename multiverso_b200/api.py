@@ -76,6 +76,19 @@ def aggregate(data):
     return host.aggregate(data)
 
 
+def symm_tensor(numel: int, dtype="float32"):
+    """A tensor that ``aggregate`` reduces in place without a staging copy: symmetric (peer-mapped, NVLS
+    multicast when available) device memory on the device backend, a plain tensor on the host backend.
+    Collective on the device backend."""
+    import torch
+    rt = _rt()
+    dt = getattr(torch, dtype) if isinstance(dtype, str) else dtype
+    if rt.backend == "device":
+        from .parallel import symm_tensor as _st
+        return _st(numel, dt)
+    return torch.empty(int(numel), dtype=dt)
+
+
 def net_bind(rank_: int, endpoint: str) -> None:
     """MV_NetBind (explicit-endpoint bootstrap of the control plane, C# path)."""
     from . import host

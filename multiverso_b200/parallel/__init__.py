@@ -1,3 +1,3 @@
-from .collectives import aggregate
+from .collectives import aggregate, symm_tensor
 
-__all__ = ["aggregate"]
+__all__ = ["aggregate", "symm_tensor"]

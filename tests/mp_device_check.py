@@ -134,6 +134,34 @@ def scenario_async():
         y = torch.full((n_el,), float(r + 1), device="cuda")
         mv.aggregate(y)
         check(f"aggregate_f32_{n_el}", torch.equal(y, torch.full((n_el,), W * (W + 1) / 2.0, device="cuda")))
+    # latency path (one fused launch, double-buffered staging): back-to-back calls, changing sizes / dtypes,
+    # interleaved with the staged large-message path
+    ok_f = True
+    for it in range(24):
+        n_el = (1, 7, 1000, 4099, 262144)[it % 5]
+        dt = (torch.float32, torch.int32, torch.float64)[it % 3]
+        v = torch.full((n_el,), r + 1 + it, device="cuda").to(dt)
+        mv.aggregate(v)
+        ok_f = ok_f and bool((v == W * (W + 1) // 2 + W * it).all())
+        if it % 8 == 7:
+            big = torch.ones(600_000, device="cuda")
+            mv.aggregate(big)
+            ok_f = ok_f and bool((big == W).all())
+    un = torch.arange(1001, device="cuda", dtype=torch.float32)[1:]      # 4-byte aligned only
+    mv.aggregate(un)
+    ok_f = ok_f and bool(torch.equal(un, W * torch.arange(1, 1001, device="cuda", dtype=torch.float32)))
+    check("aggregate_fused_small", ok_f)
+    # zero-copy aggregate on a tensor in symmetric memory, mixed with the staged path
+    zs = mv.symm_tensor(2_000_003, "float32")
+    ok_z = True
+    for it in range(3):
+        zs.fill_(float(r + 1 + it))
+        mv.aggregate(zs)
+        ok_z = ok_z and bool((zs == W * (W + 1) / 2.0 + W * it).all())
+        big = torch.ones(700_001, device="cuda")
+        mv.aggregate(big)
+        ok_z = ok_z and bool((big == W).all())
+    check("aggregate_symm_in_place", ok_z)
     z = torch.full((5_000_000,), float(r + 1), device="cuda")
     from multiverso_b200.parallel import aggregate as _agg
     _agg(z, algo="nvls")

@@ -66,6 +66,12 @@ gemm)
 ncu_gemm)
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:get_gemm_fused -s 2 -c 1 -f -o gpurun_out/get_gemm python bench/get_gemm.py --shapes 4096x65536x512 --iters 2 > gpurun_out/ncu_get_gemm.log 2>&1; echo "ncu_gemm rc=$?"
   ;;
+allreduce)
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+9)) bench/allreduce.py > gpurun_out/allreduce.log 2>&1; echo "allreduce rc=$?"; grep '^\[' gpurun_out/allreduce.log | tail -1 | python -c "
+import sys,json
+for l in sys.stdin:
+    for r in json.loads(l): print({k:(round(v,1) if isinstance(v,float) else v) for k,v in r.items()})"
+  ;;
 perf)
   if [ "$NG" -gt 1 ]; then L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+8))"; else L="python"; fi
   timeout 300 $L bench/matrix_perf.py > gpurun_out/matrix_perf.log 2>&1; echo "matrix_perf dense rc=$?"; grep '^{' gpurun_out/matrix_perf.log | tail -1 | cut -c1-500
