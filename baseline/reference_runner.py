@@ -52,7 +52,7 @@ def run_wordembedding(ref_bin: str, args) -> dict:
            "-size", str(args.dim), "-cbow", "0", "-negative", str(args.negative), "-window", str(args.window),
            "-epoch", "1", "-alpha", "0.025", "-threads", str(threads), "-min_count", "1", "-sample", "0",
            "-binary", "1", "-hs", "0", "-data_block_size", str(block_bytes), "-max_preload_data_size",
-           str(8 * block_bytes), "-stopwords", "0", "-use_adagrad", "0", "-is_pipeline", "0"]
+           str(8 * block_bytes), "-stopwords", "0", "-use_adagrad", "0", "-is_pipeline", "1"]
     env = dict(os.environ, MV_SHIM_RANK=str(rank), MV_SHIM_SIZE=str(world), OMP_NUM_THREADS=str(threads))
     t_start = t_end = None
     t_launch = time.time()
@@ -98,6 +98,8 @@ def run_wordembedding(ref_bin: str, args) -> dict:
                    "global_batch": n_words * world // 3, "seq_len": 1000,
                    "parallelism": f"{world} CPU process(es) x {threads} OpenMP threads, reference PS over the MPI shim",
                    "words_per_rank": n_words,
+                   "steps_note": "the reference CLI has no step count: a step here is one of its data blocks "
+                                 "(-data_block_size = corpus/3), the whole corpus is timed",
                    "note": "unmodified /root/reference sources (core + Applications/WordEmbedding) compiled against "
                            "baseline/mpi_shim; CPU only -- the reference has no GPU code"},
         "e2e": {"value": value, "unit": "words/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
