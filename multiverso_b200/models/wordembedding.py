@@ -209,7 +209,7 @@ class WordEmbedding:
         side = self._side
         st = self._prefetched
         self._prefetched = None
-        if st is None or st["tokens"] is not tokens:
+        if st is None or st["tokens"].data_ptr() != tokens.data_ptr() or st["tokens"].numel() != tokens.numel():
             st = self._prepare_block(tokens, wait=False)          # first block: nothing to overlap with
             self._record_streams(st, side)                        # allocated here, last used over there
         else:
