@@ -168,3 +168,32 @@ def test_checkpoint_roundtrip(mv_device, tmp_path):
     t2.load(buf)
     assert torch.equal(t2.get(), want)
     assert torch.equal(t2.state[0], t.state[0])
+
+
+@pytest.mark.gpu
+def test_watchdog_reports_dead_peer(mv_device):
+    """Fault injection: a device-side wait on a flag that nobody will ever write must end
+    with a diagnostic naming the channel / peer after -barrier_timeout_s, not hang the GPU."""
+    import ctypes as C
+    import time
+    from multiverso_b200 import _native as N
+    from multiverso_b200.runtime import Runtime
+    from multiverso_b200.utils.log import FatalError, Log
+    rt = Runtime.get()
+    ch = rt.new_channels(1)
+    kill, Log.kill_fatal = Log.kill_fatal, False
+    try:
+        t0 = time.time()
+        N.check(N.cuda_lib().mvb_wait(rt.pads_array(), rt.rank, rt.size, ch, C.c_uint64(7), C.c_uint32(1),
+                                      C.c_void_p(rt.err_flag.data_ptr()), C.c_double(0.05),
+                                      C.c_void_p(N.stream_ptr())), "mvb_wait")
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 10.0                     # gave up after the budget, did not spin forever
+        with pytest.raises(FatalError, match="watchdog"):
+            rt.check_watchdog()
+        rt.check_watchdog()                                # the flag is cleared: the runtime stays usable
+        t = mv_device.ArrayTable(1000, "float32")
+        t.add(torch.ones(1000, device="cuda"))
+        assert bool((t.get() == 1).all())
+    finally:
+        Log.kill_fatal = kill
