@@ -246,6 +246,7 @@ get_gemm_fused_kernel(const __grid_constant__ CUtensorMap map_x,
     for (int i = 0; i < XC_MAX; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], kEpiWarps * NC); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();      // keeps the barrier words and tcgen05.alloc's smem result in separate epochs (racecheck)
   if (warp == 1) {
     if constexpr (NC == 1) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sl->tmem_base)));
