@@ -45,7 +45,8 @@ class Reader {
     eof_ = false;
     Start();
   }
-  // pops up to max samples; returns 0 only when the epoch is exhausted
+  // pops up to max samples; returns 0 only when the epoch is exhausted, and -(nnz of the next
+  // sample) when not even one sample fits into max_nnz (the caller grows its buffers and retries)
   int64_t Next(int64_t max_samples, int64_t max_nnz, int64_t* row_ptr, int64_t* keys, float* vals,
                float* labels, float* weights) {
     int64_t n = 0, nnz = 0;
@@ -55,7 +56,10 @@ class Reader {
       cv_.wait(lk, [&] { return !queue_.empty() || eof_; });
       if (queue_.empty()) break;
       Sample& s = queue_.front();
-      if (nnz + static_cast<int64_t>(s.keys.size()) > max_nnz) break;
+      if (nnz + static_cast<int64_t>(s.keys.size()) > max_nnz) {
+        if (n == 0) return -static_cast<int64_t>(s.keys.size());
+        break;
+      }
       std::copy(s.keys.begin(), s.keys.end(), keys + nnz);
       std::copy(s.vals.begin(), s.vals.end(), vals + nnz);
       nnz += static_cast<int64_t>(s.keys.size());

@@ -44,7 +44,8 @@ int MVA_HuffmanBuild(const int64_t* freq, int n, int max_code, int32_t* points, 
  * A background thread parses into a bounded queue of `buffer_samples`. */
 void* MVA_LRReaderOpen(const char* files, const char* reader_type, int sparse, int64_t input_size,
                        int buffer_samples);
-/* Fills CSR arrays for up to max_samples samples; returns the number of samples (0 = epoch end) */
+/* Fills CSR arrays for up to max_samples samples; returns the number of samples, 0 at the end of
+ * the epoch, or -(nnz of the next sample) when max_nnz cannot hold even one sample */
 int64_t MVA_LRReaderNext(void* reader, int64_t max_samples, int64_t max_nnz, int64_t* row_ptr,
                          int64_t* keys, float* vals, float* labels, float* weights);
 void MVA_LRReaderReset(void* reader);

@@ -44,14 +44,18 @@ class SampleReader:
     def next(self, max_samples: int, max_nnz: Optional[int] = None):
         max_nnz = max_nnz or max_samples * min(self.input_size + 1, 4096)
         row_ptr = np.zeros(max_samples + 1, np.int64)
-        keys = np.empty(max_nnz, np.int64)
-        vals = np.empty(max_nnz, np.float32)
         labels = np.empty(max_samples, np.float32)
         weights = np.empty(max_samples, np.float32)
-        n = lib().MVA_LRReaderNext(self.h, max_samples, max_nnz, row_ptr.ctypes.data_as(C.c_void_p),
-                                   keys.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p),
-                                   labels.ctypes.data_as(C.c_void_p), weights.ctypes.data_as(C.c_void_p))
-        if n <= 0:
+        while True:
+            keys = np.empty(max_nnz, np.int64)
+            vals = np.empty(max_nnz, np.float32)
+            n = lib().MVA_LRReaderNext(self.h, max_samples, max_nnz, row_ptr.ctypes.data_as(C.c_void_p),
+                                       keys.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p),
+                                       labels.ctypes.data_as(C.c_void_p), weights.ctypes.data_as(C.c_void_p))
+            if n >= 0:
+                break
+            max_nnz = max(2 * max_nnz, -n)      # one sample is wider than the buffer: grow and retry
+        if n == 0:
             return None
         nnz = int(row_ptr[n])
         return row_ptr[:n + 1], keys[:nnz], vals[:nnz], labels[:n], weights[:n]
