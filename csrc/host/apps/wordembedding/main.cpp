@@ -12,8 +12,6 @@
 //
 // The GPU implementation of the same application is multiverso_b200/apps/wordembedding.py
 // (sm_100a kernels, HBM-resident tables); this binary is the CPU plumbing mode.
-#include <omp.h>
-
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>

@@ -1,6 +1,8 @@
 #include "trainer.h"
 
+#ifdef _OPENMP
 #include <omp.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -167,7 +169,11 @@ TrainStats Trainer::Train(DataBlock* b, int64_t words_before, int num_workers, i
   const double block_words = static_cast<double>(b->corpus_words) * std::max(1, num_workers);
 #pragma omp parallel num_threads(threads)
   {
+#ifdef _OPENMP
     const int tid = omp_get_thread_num(), nth = omp_get_num_threads();
+#else
+    const int tid = 0, nth = 1;
+#endif
     Scratch s;
     s.hidden.resize(opt_.embeding_size);
     s.hidden_err.resize(opt_.embeding_size);
