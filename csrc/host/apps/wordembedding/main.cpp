@@ -80,14 +80,15 @@ class BlockQueue {
 };
 
 // Reads the corpus `epochs` times in blocks of `block_tokens` ids; this rank keeps the blocks
-// i with i % size == rank.
+// i with i % size == rank (i counts over the whole run).
 void LoaderMain(void* dict, const Option& opt, int rank, int size, int64_t block_tokens, BlockQueue* q) {
   const std::string sw = (opt.stopwords && !opt.sw_file.empty()) ? opt.sw_file : "";
   void* corpus = MVA_CorpusOpen(dict, opt.train_file.c_str(), sw.c_str(), opt.sample, 12345 + rank);
   if (corpus == nullptr) Log::Fatal("cannot open the corpus %s\n", opt.train_file.c_str());
+  int64_t i = 0;                             // blocks are dealt round-robin across epoch boundaries
   for (int epoch = 0; epoch < opt.epoch; ++epoch) {
     if (epoch > 0) MVA_CorpusReset(corpus);
-    for (int64_t i = 0;; ++i) {
+    for (;; ++i) {
       auto b = std::make_unique<DataBlock>();
       b->tokens.resize(block_tokens);
       int64_t words = 0;

@@ -8,6 +8,29 @@ from .. import _native as N
 _lib = None
 
 
+def run_native(app: str, argv) -> dict:
+    """Run the native build/bin/<app> (CPU workers / servers on the host runtime) with `argv`
+    and return the JSON result line it prints -- what the Python app drivers fall back to
+    when there is no GPU.  Under a rank launcher (tools/mvrun.py, torchrun) every rank execs
+    its own copy; the host runtime bootstraps from the inherited MV_RANK / MV_SIZE / MV_PORT
+    (or RANK / WORLD_SIZE / MASTER_PORT) environment."""
+    import json
+    import subprocess
+    from .. import _build
+    _build.build_host()
+    exe = _build.BUILD / "bin" / app
+    p = subprocess.run([str(exe), *map(str, argv)], stdout=subprocess.PIPE, text=True)
+    stats = {}
+    for line in p.stdout.splitlines():
+        if line.startswith("{"):
+            stats = json.loads(line)
+        else:
+            print(line)
+    if p.returncode != 0:
+        raise RuntimeError(f"{exe} exited with {p.returncode}")
+    return stats
+
+
 def lib():
     global _lib
     if _lib is None:

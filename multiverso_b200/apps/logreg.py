@@ -181,6 +181,11 @@ class LogReg:
 
 
 def run(config_file: str) -> dict:
+    import torch
+    if not torch.cuda.is_available():
+        # no GPU: the native CPU implementation of the same application (csrc/host/apps/logreg)
+        from ._applib import run_native
+        return run_native("logreg", [config_file])
     from ..models.logreg import LogRegConfig
     import multiverso_b200 as mv
     cfg = LogRegConfig.from_file(config_file)

@@ -24,6 +24,8 @@ import numpy as np
 from ..utils import Log
 from ._applib import lib
 
+# The CPU implementation of this application is the native binary build/bin/wordembedding
+# (csrc/host/apps/wordembedding); run() execs it when there is no GPU.
 FLAG_HELP = """-size <int> -train_file <file> -endpoints_file <file> -read_vocab <file> -binary <0|1|2>
 -cbow <0|1> -alpha <float> -output <file> -window <int> -sample <float> -hs <0|1>
 -data_block_size <bytes> -max_preload_data_size <bytes> -negative <int> -threads <int>
@@ -108,9 +110,9 @@ class BlockLoader(threading.Thread):
     def run(self):
         import torch
         L = lib()
+        i = 0                                       # blocks are dealt round-robin across epoch boundaries
         for ep in range(self.epochs):
             L.MVA_CorpusReset(self.c)
-            i = 0
             while True:
                 buf = torch.empty(self.block_tokens, dtype=torch.int32).pin_memory() \
                     if torch.cuda.is_available() else torch.empty(self.block_tokens, dtype=torch.int32)
@@ -134,6 +136,10 @@ def run(argv: List[str]) -> dict:
     if not opt.train_file:
         print("usage: wordembedding " + FLAG_HELP)
         return {}
+    if not torch.cuda.is_available():
+        # no GPU: the native CPU implementation of the same application (csrc/host/apps/wordembedding)
+        from ._applib import run_native
+        return run_native("wordembedding", argv)
     mv.init()
     rank, size = mv.rank(), mv.size()
     t0 = time.time()
