@@ -41,7 +41,7 @@ Stream* StreamFactory::GetStream(const URI& uri, FileOpenMode mode) {
   if (it == inst.end()) {
     std::unique_ptr<StreamFactory> f;
     if (uri.scheme == "file") f.reset(new LocalStreamFactory());
-    else if (uri.scheme == "hdfs") f.reset(new HDFSStreamFactory());
+    else if (uri.scheme == "hdfs") f.reset(new HDFSStreamFactory(uri.host));
     else {
       Log::Error("StreamFactory: unsupported scheme '%s'", uri.scheme.c_str());
       return nullptr;
@@ -49,12 +49,6 @@ Stream* StreamFactory::GetStream(const URI& uri, FileOpenMode mode) {
     it = inst.emplace(key, std::move(f)).first;
   }
   return it->second->Open(uri, mode);
-}
-
-Stream* HDFSStreamFactory::Open(const URI& uri, FileOpenMode) {
-  Log::Error("hdfs://%s%s: HDFS support is not built (no libhdfs in this environment)",
-             uri.host.c_str(), uri.name.c_str());
-  return nullptr;
 }
 
 TextReader::TextReader(const URI& uri, size_t buf_size)

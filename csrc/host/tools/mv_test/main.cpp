@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <unistd.h>
@@ -548,9 +549,48 @@ static void TestAppTables() {   // LogReg SparseTable / FTRLTable (sparse_table.
   MV_ShutDown();
 }
 
+// Round trip through StreamFactory for any URI scheme: write 3 MB + a text tail, append, read
+// back with Stream::Read and TextReader (used with hdfs:// against a stand-in libhdfs).
+static void TestStream(const std::string& uri) {
+  std::vector<int> payload(750000);
+  std::iota(payload.begin(), payload.end(), 7);
+  {
+    std::unique_ptr<Stream> w(StreamFactory::GetStream(URI(uri), FileOpenMode::BinaryWrite));
+    EXPECT(w != nullptr && w->Good());
+    if (!w) return;
+    w->Write(payload.data(), payload.size() * sizeof(int));
+    w->Flush();
+  }
+  {
+    std::unique_ptr<Stream> a(StreamFactory::GetStream(URI(uri), FileOpenMode::BinaryAppend));
+    EXPECT(a != nullptr && a->Good());
+    const char tail[] = "\nfirst line\nsecond line\n";
+    if (a) a->Write(tail, sizeof tail - 1);
+  }
+  {
+    std::unique_ptr<Stream> r(StreamFactory::GetStream(URI(uri), FileOpenMode::BinaryRead));
+    EXPECT(r != nullptr && r->Good());
+    if (!r) return;
+    std::vector<int> back(payload.size());
+    EXPECT(r->Read(back.data(), back.size() * sizeof(int)) == back.size() * sizeof(int));
+    EXPECT(back == payload);
+    char rest[64] = {0};
+    EXPECT(r->Read(rest, sizeof rest) == 24);   // short read at the end of the file
+  }
+  TextReader reader(URI(uri), 1 << 12);
+  std::string line, last, before_last;
+  while (reader.GetLine(line)) {
+    before_last = last;
+    last = line;
+  }
+  EXPECT(before_last == "first line" && last == "second line");
+  EXPECT(StreamFactory::GetStream(URI(uri + ".missing"), FileOpenMode::Read) == nullptr ||
+         !std::unique_ptr<Stream>(StreamFactory::GetStream(URI(uri + ".missing"), FileOpenMode::Read))->Good());
+}
+
 int main(int argc, char* argv[]) {
   if (argc < 2) {
-    fprintf(stderr, "usage: mv_test unit|kv|array|array_async|net|matrix|sparse|allreduce|apptables|dense_perf [rows]|sparse_perf [rows]|updater:<name> [-flag=value ...]\n");
+    fprintf(stderr, "usage: mv_test unit|kv|array|array_async|net|matrix|sparse|allreduce|apptables|dense_perf [rows]|sparse_perf [rows]|updater:<name>|stream <uri> [-flag=value ...]\n");
     return 2;
   }
   std::string which = argv[1];
@@ -567,6 +607,7 @@ int main(int argc, char* argv[]) {
   else if (which == "dense_perf" || which == "sparse_perf")
     TestMatrixPerf(which == "sparse_perf", argc > 2 ? atoi(argv[2]) : 100000);
   else if (which.rfind("updater:", 0) == 0) TestUpdatersAndCheckpoint(which.substr(8));
+  else if (which == "stream" && argc > 2) TestStream(argv[2]);
   else { fprintf(stderr, "unknown test %s\n", which.c_str()); return 2; }
   printf("[mv_test %s] %s\n", which.c_str(), g_fail ? "FAIL" : "PASS");
   return g_fail ? 1 : 0;

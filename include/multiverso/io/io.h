@@ -1,7 +1,6 @@
 // IO streams (counterpart of include/multiverso/io/io.h:24-132): URI, Stream,
 // StreamFactory::GetStream(uri, mode), TextReader::GetLine. "file" scheme = LocalStream;
-// "hdfs" is recognised but unavailable (no libhdfs in the image; the reference's own HDFS
-// stream does not compile either).
+// "hdfs" = HDFSStream over a run-time loaded libhdfs (io/hdfs_stream.h).
 #ifndef MULTIVERSO_IO_IO_H_
 #define MULTIVERSO_IO_IO_H_
 #include <cstddef>
