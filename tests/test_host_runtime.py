@@ -98,3 +98,20 @@ def test_hdfs_stream(tmp_path):
     r = subprocess.run([BIN, "stream", "hdfs://namenode:9000/models/x.bin"], capture_output=True, text=True,
                        timeout=60, env=env)
     assert r.returncode != 0 and "libhdfs.so not found" in (r.stdout + r.stderr)
+
+
+def test_explicit_endpoint_bootstrap():
+    # MV_NetBind / MV_NetConnect before MV_Init (C# binding path)
+    out = run_mp(3, sys.executable, os.path.join(ROOT, "tests", "mp_host_netbind.py"))
+    assert out.count("netbind ok") == 3
+
+
+def test_machine_file_bootstrap(tmp_path):
+    # -machine_file / -port (ZeroMQ-style bootstrap of the reference, zmq_net.h:25-61): one
+    # address per line; several ranks on one host take consecutive ports and MV_RANK picks the line
+    import random
+    mf = tmp_path / "machines.txt"
+    mf.write_text("127.0.0.1\n127.0.0.1\n127.0.0.1\n")
+    port = random.randint(20000, 50000)
+    out = run_mp(3, BIN, "array", f"-machine_file={mf}", f"-port={port}")
+    assert out.count("PASS") == 3
