@@ -196,6 +196,7 @@ int main(int argc, char* argv[]) {
          last_acc, test_error, epoch_losses.c_str());
   fflush(stdout);
   multiverso::MV_Barrier();
+  model.reset();                            // worker tables go before the runtime
   multiverso::MV_ShutDown();
   return 0;
 }

@@ -279,11 +279,11 @@ void Model::LogTimes() const {
 PSModel::PSModel(const Configure& config) : Model(config) {
   using namespace multiverso;
   if (ftrl_) {
-    ftrl_table_ = MV_CreateTable(FTRLTableOption<float>(static_cast<size_t>(size_)));
+    ftrl_table_.reset(MV_CreateTable(FTRLTableOption<float>(static_cast<size_t>(size_))));
   } else if (cfg_.sparse) {
-    sparse_ = MV_CreateTable(SparseTableOption<float>(static_cast<size_t>(size_)));
+    sparse_.reset(MV_CreateTable(SparseTableOption<float>(static_cast<size_t>(size_))));
   } else {
-    dense_ = MV_CreateTable(ArrayTableOption<float>(static_cast<size_t>(size_)));
+    dense_.reset(MV_CreateTable(ArrayTableOption<float>(static_cast<size_t>(size_))));
     next_w_.assign(size_, 0.0f);
   }
   if (dense_ == nullptr && sparse_ == nullptr && ftrl_table_ == nullptr)

@@ -121,9 +121,10 @@ class PSModel : public Model {
   void StartSparsePull(const std::vector<int64_t>& feature_keys, SparsePull* p);
   void FinishSparsePull(SparsePull* p);
 
-  multiverso::ArrayWorker<float>* dense_ = nullptr;
-  multiverso::SparseWorkerTable<float>* sparse_ = nullptr;
-  multiverso::FTRLWorkerTable<float>* ftrl_table_ = nullptr;
+  // exactly one of the three exists; the worker half belongs to its creator
+  std::unique_ptr<multiverso::ArrayWorker<float>> dense_;
+  std::unique_ptr<multiverso::SparseWorkerTable<float>> sparse_;
+  std::unique_ptr<multiverso::FTRLWorkerTable<float>> ftrl_table_;
   std::vector<float> next_w_;          // dense double buffer
   int dense_pending_ = -1;
   SparsePull pending_;                 // sparse double buffer (next window)

@@ -170,7 +170,8 @@ int main(int argc, char* argv[]) {
               static_cast<long long>(vocab.total_words), size, opt.thread_cnt);
   }
 
-  ParamStore store(opt, vocab.size);
+  auto store_owner = std::make_unique<ParamStore>(opt, vocab.size);
+  ParamStore& store = *store_owner;
   Trainer trainer(opt, vocab);
   const int64_t block_tokens = std::max<int64_t>(1024, opt.data_block_size / kBytesPerToken);
   BlockQueue queue(opt.max_preload_data_size);
@@ -230,6 +231,7 @@ int main(int argc, char* argv[]) {
          store.pull_seconds(), store.push_seconds(), my_words / std::max(seconds, 1e-9), losses.c_str());
   fflush(stdout);
   multiverso::MV_Barrier();
+  store_owner.reset();                      // worker tables go before the runtime
   multiverso::MV_ShutDown();
   MVA_DictFree(dict);
   return 0;

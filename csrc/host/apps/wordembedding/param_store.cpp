@@ -10,13 +10,13 @@ using namespace multiverso;
 
 ParamStore::ParamStore(const Option& option, int vocab_size) : opt_(option), dim_(option.embeding_size) {
   const float r = 0.5f / dim_;
-  input_ = MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_, -r, r));
-  output_ = MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_));
+  input_.reset(MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_, -r, r)));
+  output_.reset(MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_)));
   if (opt_.use_adagrad) {
-    input_g2_ = MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_));
-    output_g2_ = MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_));
+    input_g2_.reset(MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_)));
+    output_g2_.reset(MV_CreateTable(MatrixTableOption<float>(vocab_size, dim_)));
   }
-  word_count_ = MV_CreateTable(KVTableOption<int, int64_t>());
+  word_count_.reset(MV_CreateTable(KVTableOption<int, int64_t>()));
   if (input_ == nullptr || word_count_ == nullptr)
     Log::Fatal("wordembedding: every rank must be a worker (run with the default -ps_role)\n");
 }
@@ -29,11 +29,11 @@ void ParamStore::PullRows(Table* t, RowCache* cache, std::vector<float>* dst) {
 
 void ParamStore::Pull(DataBlock* b) {
   Timer timer;
-  PullRows(input_, &b->input, &b->input.rows);
-  PullRows(output_, &b->output, &b->output.rows);
+  PullRows(input_.get(), &b->input, &b->input.rows);
+  PullRows(output_.get(), &b->output, &b->output.rows);
   if (opt_.use_adagrad) {
-    PullRows(input_g2_, &b->input, &b->input.g2);
-    PullRows(output_g2_, &b->output, &b->output.g2);
+    PullRows(input_g2_.get(), &b->input, &b->input.g2);
+    PullRows(output_g2_.get(), &b->output, &b->output.g2);
   }
   pull_s_ += timer.elapse() * 1e-3;
 }
@@ -50,11 +50,11 @@ void ParamStore::PushRows(Table* t, const RowCache& cache, const std::vector<flo
 
 void ParamStore::PushDelta(DataBlock* b) {
   Timer timer;
-  PushRows(input_, b->input, b->input.rows);
-  PushRows(output_, b->output, b->output.rows);
+  PushRows(input_.get(), b->input, b->input.rows);
+  PushRows(output_.get(), b->output, b->output.rows);
   if (opt_.use_adagrad) {
-    PushRows(input_g2_, b->input, b->input.g2);
-    PushRows(output_g2_, b->output, b->output.g2);
+    PushRows(input_g2_.get(), b->input, b->input.g2);
+    PushRows(output_g2_.get(), b->output, b->output.g2);
   }
   push_s_ += timer.elapse() * 1e-3;
 }

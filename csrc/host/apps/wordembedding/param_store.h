@@ -6,6 +6,7 @@
 #ifndef MVAPP_WORDEMBEDDING_PARAM_STORE_H_
 #define MVAPP_WORDEMBEDDING_PARAM_STORE_H_
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "data_block.h"
@@ -44,11 +45,9 @@ class ParamStore {
   void PushRows(Table* t, const RowCache& cache, const std::vector<float>& trained);
   const Option& opt_;
   int dim_;
-  Table* input_ = nullptr;
-  Table* output_ = nullptr;
-  Table* input_g2_ = nullptr;
-  Table* output_g2_ = nullptr;
-  multiverso::KVWorkerTable<int, int64_t>* word_count_ = nullptr;
+  // the worker halves belong to the creator (the server halves to the runtime)
+  std::unique_ptr<Table> input_, output_, input_g2_, output_g2_;
+  std::unique_ptr<multiverso::KVWorkerTable<int, int64_t>> word_count_;
   double pull_s_ = 0, push_s_ = 0;
 };
 
