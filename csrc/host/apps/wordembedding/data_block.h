@@ -6,6 +6,7 @@
 #ifndef MVAPP_WORDEMBEDDING_DATA_BLOCK_H_
 #define MVAPP_WORDEMBEDDING_DATA_BLOCK_H_
 #include <cstdint>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -15,12 +16,33 @@ namespace wordembedding {
 
 using multiverso::integer_t;
 
+// Float array that is NOT value-initialised on allocation: row caches are hundreds of MB per
+// block and are overwritten in full by the pull that follows, so the zero fill (and its page
+// faults on the calling thread) would be pure overhead.
+class FloatBuffer {
+ public:
+  void Allocate(size_t n) {
+    if (n > capacity_) {
+      data_.reset(new float[n]);
+      capacity_ = n;
+    }
+    size_ = n;
+  }
+  float* data() { return data_.get(); }
+  const float* data() const { return data_.get(); }
+  size_t size() const { return size_; }
+
+ private:
+  std::unique_ptr<float[]> data_;
+  size_t size_ = 0, capacity_ = 0;
+};
+
 // A set of table rows cached locally: sorted unique row ids, the values as pulled (trained in
 // place) and, with AdaGrad, the accumulated squared gradients.
 struct RowCache {
   std::vector<integer_t> ids;
-  std::vector<float> rows;      // ids.size() x dim
-  std::vector<float> g2;        // ids.size() x dim when AdaGrad, else empty
+  FloatBuffer rows;             // ids.size() x dim
+  FloatBuffer g2;               // ids.size() x dim when AdaGrad, else empty
   size_t size() const { return ids.size(); }
 };
 

@@ -25,6 +25,7 @@
 
 #include "data_block.h"
 #include "multiverso/apps/app_api.h"
+#include "multiverso/dashboard.h"
 #include "multiverso/multiverso.h"
 #include "multiverso/util/log.h"
 #include "multiverso/util/timer.h"
@@ -230,6 +231,7 @@ int main(int argc, char* argv[]) {
          rank, size, vocab.size, static_cast<long long>(my_words), static_cast<long long>(blocks), seconds, train_s,
          store.pull_seconds(), store.push_seconds(), my_words / std::max(seconds, 1e-9), losses.c_str());
   fflush(stdout);
+  if (rank == 0) multiverso::Dashboard::Display();   // per-hook timing of the table operations
   multiverso::MV_Barrier();
   store_owner.reset();                      // worker tables go before the runtime
   multiverso::MV_ShutDown();

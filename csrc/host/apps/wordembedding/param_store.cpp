@@ -21,8 +21,8 @@ ParamStore::ParamStore(const Option& option, int vocab_size) : opt_(option), dim
     Log::Fatal("wordembedding: every rank must be a worker (run with the default -ps_role)\n");
 }
 
-void ParamStore::PullRows(Table* t, RowCache* cache, std::vector<float>* dst) {
-  dst->resize(cache->size() * dim_);
+void ParamStore::PullRows(Table* t, RowCache* cache, FloatBuffer* dst) {
+  dst->Allocate(cache->size() * dim_);
   if (cache->size() == 0) return;
   t->Get(dst->data(), dst->size(), cache->ids.data(), static_cast<int>(cache->size()));
 }
@@ -38,14 +38,18 @@ void ParamStore::Pull(DataBlock* b) {
   pull_s_ += timer.elapse() * 1e-3;
 }
 
-void ParamStore::PushRows(Table* t, const RowCache& cache, const std::vector<float>& trained) {
+void ParamStore::PushRows(Table* t, const RowCache& cache, const FloatBuffer& trained) {
   if (cache.size() == 0) return;
-  std::vector<float> delta(trained.size());
+  delta_.Allocate(trained.size());
+  float* delta = delta_.data();
+  const float* mine = trained.data();
   std::vector<integer_t> ids(cache.ids);
-  t->Get(delta.data(), delta.size(), ids.data(), static_cast<int>(ids.size()));   // server now
+  t->Get(delta, delta_.size(), ids.data(), static_cast<int>(ids.size()));   // server now
   const float inv = 1.0f / MV_NumWorkers();
-  for (size_t i = 0; i < delta.size(); ++i) delta[i] = (trained[i] - delta[i]) * inv;
-  t->Add(delta.data(), delta.size(), ids.data(), static_cast<int>(ids.size()));
+  const long long n = static_cast<long long>(delta_.size());
+#pragma omp parallel for schedule(static) num_threads(opt_.thread_cnt) if (n > (1 << 16))
+  for (long long i = 0; i < n; ++i) delta[i] = (mine[i] - delta[i]) * inv;
+  t->Add(delta, delta_.size(), ids.data(), static_cast<int>(ids.size()));
 }
 
 void ParamStore::PushDelta(DataBlock* b) {

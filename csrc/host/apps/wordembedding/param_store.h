@@ -41,13 +41,14 @@ class ParamStore {
 
  private:
   using Table = multiverso::MatrixWorkerTable<float>;
-  void PullRows(Table* t, RowCache* cache, std::vector<float>* dst);
-  void PushRows(Table* t, const RowCache& cache, const std::vector<float>& trained);
+  void PullRows(Table* t, RowCache* cache, FloatBuffer* dst);
+  void PushRows(Table* t, const RowCache& cache, const FloatBuffer& trained);
   const Option& opt_;
   int dim_;
   // the worker halves belong to the creator (the server halves to the runtime)
   std::unique_ptr<Table> input_, output_, input_g2_, output_g2_;
   std::unique_ptr<multiverso::KVWorkerTable<int, int64_t>> word_count_;
+  FloatBuffer delta_;            // scratch of PushRows (only the training thread pushes)
   double pull_s_ = 0, push_s_ = 0;
 };
 

@@ -3,13 +3,20 @@
 #include <algorithm>
 #include <random>
 #include "multiverso/multiverso.h"
+#include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
 
 namespace multiverso {
 
+MV_DECLARE_int(omp_threads);
+
 namespace {
 const integer_t kWholeTable = -1;
 inline bool IsWhole(const Blob& keys) { return keys.size<integer_t>() == 1 && keys.As<integer_t>(0) == kWholeTable; }
+// Row loops (gather / scatter / per-row update) go parallel above this many rows; they are
+// random accesses over the shard, so extra threads buy memory-level parallelism.
+constexpr long long kParallelRows = 2048;
+inline int RowThreads(long long rows) { return rows >= kParallelRows ? std::max(1, MV_CONFIG(omp_threads)) : 1; }
 }  // namespace
 
 RowPartition::RowPartition(integer_t rows, int servers) : num_row(rows) {
@@ -40,7 +47,23 @@ MatrixWorkerTable<T>::MatrixWorkerTable(integer_t num_row, integer_t num_col)
 }
 
 template <typename T>
+void MatrixWorkerTable<T>::GetRecord::Seal() {
+  auto by_row = [](const std::pair<integer_t, T*>& a, const std::pair<integer_t, T*>& b) { return a.first < b.first; };
+  if (!std::is_sorted(rows.begin(), rows.end(), by_row)) std::stable_sort(rows.begin(), rows.end(), by_row);
+}
+
+template <typename T>
+T* MatrixWorkerTable<T>::GetRecord::Find(integer_t row) const {
+  // the last entry of a run of equal ids wins, like repeated assignment into a map
+  auto it = std::upper_bound(rows.begin(), rows.end(), row,
+                             [](integer_t r, const std::pair<integer_t, T*>& e) { return r < e.first; });
+  if (it == rows.begin() || (it - 1)->first != row) return nullptr;
+  return (it - 1)->second;
+}
+
+template <typename T>
 int MatrixWorkerTable<T>::SubmitGet(GetRecord&& rec, Blob keys, const GetOption* opt) {
+  rec.Seal();
   const int id = NewRequest();
   {
     std::lock_guard<std::mutex> lk(rec_mu_);
@@ -68,7 +91,7 @@ template <typename T>
 int MatrixWorkerTable<T>::GetAsync(integer_t row_id, T* data, size_t size, const GetOption* opt) {
   CHECK(size == static_cast<size_t>(num_col_) && row_id >= 0 && row_id < num_row_);
   GetRecord rec;
-  rec.rows[row_id] = data;
+  rec.AddRow(row_id, data);
   return SubmitGet(std::move(rec), Blob(&row_id, sizeof(integer_t)), opt);
 }
 template <typename T>
@@ -76,14 +99,16 @@ int MatrixWorkerTable<T>::GetAsync(const std::vector<integer_t>& row_ids, const 
                                    size_t size, const GetOption* opt) {
   CHECK(size == static_cast<size_t>(num_col_) && row_ids.size() == data_vec.size());
   GetRecord rec;
-  for (size_t i = 0; i < row_ids.size(); ++i) rec.rows[row_ids[i]] = data_vec[i];
+  rec.rows.reserve(row_ids.size());
+  for (size_t i = 0; i < row_ids.size(); ++i) rec.AddRow(row_ids[i], data_vec[i]);
   return SubmitGet(std::move(rec), Blob(row_ids.data(), row_ids.size() * sizeof(integer_t)), opt);
 }
 template <typename T>
 int MatrixWorkerTable<T>::GetAsync(T* data, size_t size, integer_t* row_ids, int n, const GetOption* opt) {
   CHECK(size == static_cast<size_t>(n) * num_col_);
   GetRecord rec;
-  for (int i = 0; i < n; ++i) rec.rows[row_ids[i]] = data + static_cast<size_t>(i) * num_col_;
+  rec.rows.reserve(n);
+  for (int i = 0; i < n; ++i) rec.AddRow(row_ids[i], data + static_cast<size_t>(i) * num_col_);
   return SubmitGet(std::move(rec), Blob(row_ids, sizeof(integer_t) * n), opt);
 }
 
@@ -112,7 +137,9 @@ int MatrixWorkerTable<T>::AddAsync(const std::vector<integer_t>& row_ids, const 
                                    size_t size, const AddOption* opt) {
   CHECK(size == static_cast<size_t>(num_col_) && row_ids.size() == data_vec.size());
   Blob vals(row_ids.size() * num_col_ * sizeof(T));
-  for (size_t i = 0; i < row_ids.size(); ++i)
+  const long long rows = static_cast<long long>(row_ids.size());
+#pragma omp parallel for schedule(static) num_threads(RowThreads(rows))
+  for (long long i = 0; i < rows; ++i)
     std::memcpy(vals.data() + i * num_col_ * sizeof(T), data_vec[i], num_col_ * sizeof(T));
   return WorkerTable::AddAsync(Blob(row_ids.data(), row_ids.size() * sizeof(integer_t)), std::move(vals), opt);
 }
@@ -146,24 +173,42 @@ int MatrixWorkerTable<T>::Partition(const std::vector<Blob>& kv, MsgType type,
     }
   } else {
     const size_t n = keys.size<integer_t>();
-    std::unordered_map<int, std::vector<size_t>> bucket;
+    std::vector<std::vector<size_t>> bucket(part_.num_servers);
+    int used = 0, only = -1;
     for (size_t i = 0; i < n; ++i) {
       const integer_t r = keys.As<integer_t>(i);
       CHECK(r >= 0 && r < num_row_);
-      bucket[part_.ServerOf(r)].push_back(i);
-    }
-    for (auto& b : bucket) {
-      Blob ids(b.second.size() * sizeof(integer_t));
-      for (size_t j = 0; j < b.second.size(); ++j) ids.As<integer_t>(j) = keys.As<integer_t>(b.second[j]);
-      std::vector<Blob>& v = (*out)[b.first];
-      v.push_back(std::move(ids));
-      if (is_add) {
-        Blob vals(b.second.size() * row_bytes);
-        for (size_t j = 0; j < b.second.size(); ++j)
-          std::memcpy(vals.data() + j * row_bytes, kv[1].data() + b.second[j] * row_bytes, row_bytes);
-        v.push_back(std::move(vals));
+      std::vector<size_t>& b = bucket[part_.ServerOf(r)];
+      if (b.empty()) {
+        ++used;
+        only = part_.ServerOf(r);
       }
+      b.push_back(i);
+    }
+    if (used == 1) {
+      // every row lives on one server: forward the caller's blobs as they are (no repacking)
+      std::vector<Blob>& v = (*out)[only];
+      v.push_back(keys);
+      if (is_add) v.push_back(kv[1]);
       if (option) v.push_back(*option);
+    } else {
+      for (int srv = 0; srv < part_.num_servers; ++srv) {
+        const std::vector<size_t>& b = bucket[srv];
+        if (b.empty()) continue;
+        const long long rows = static_cast<long long>(b.size());
+        Blob ids(b.size() * sizeof(integer_t));
+        for (size_t j = 0; j < b.size(); ++j) ids.As<integer_t>(j) = keys.As<integer_t>(b[j]);
+        std::vector<Blob>& v = (*out)[srv];
+        v.push_back(std::move(ids));
+        if (is_add) {
+          Blob vals(b.size() * row_bytes);
+#pragma omp parallel for schedule(static) num_threads(RowThreads(rows))
+          for (long long j = 0; j < rows; ++j)
+            std::memcpy(vals.data() + j * row_bytes, kv[1].data() + b[j] * row_bytes, row_bytes);
+          v.push_back(std::move(vals));
+        }
+        if (option) v.push_back(*option);
+      }
     }
   }
   if (is_add)
@@ -184,14 +229,13 @@ void MatrixWorkerTable<T>::ProcessReplyGet(std::vector<Blob>& reply, int msg_id)
     std::memcpy(rec.whole + part_.row_begin[sid] * num_col_, reply[1].data(), reply[1].size());
     return;
   }
-  const size_t n = keys.size<integer_t>();
-  CHECK(reply[1].size() == n * row_bytes);
-  for (size_t i = 0; i < n; ++i) {
+  const long long n = static_cast<long long>(keys.size<integer_t>());
+  CHECK(reply[1].size() == static_cast<size_t>(n) * row_bytes);
+#pragma omp parallel for schedule(static) num_threads(RowThreads(n))
+  for (long long i = 0; i < n; ++i) {
     const integer_t r = keys.As<integer_t>(i);
-    T* dst = nullptr;
-    auto it = rec.rows.find(r);
-    if (it != rec.rows.end()) dst = it->second;
-    else if (rec.whole) dst = rec.whole + r * num_col_;   // sparse delta-pull into the whole buffer
+    T* dst = rec.Find(r);
+    if (dst == nullptr && rec.whole) dst = rec.whole + r * num_col_;   // sparse delta-pull into the whole buffer
     if (dst) std::memcpy(dst, reply[1].data() + i * row_bytes, row_bytes);
   }
 }
@@ -252,12 +296,21 @@ void MatrixServerTable<T>::ProcessAdd(const std::vector<Blob>& data) {
     updater_->Update(storage_.size(), storage_.data(), vals, &opt, 0);
     return;
   }
-  const size_t n = keys.size<integer_t>();
-  CHECK(data[1].size() == n * num_col_ * sizeof(T));
-  for (size_t i = 0; i < n; ++i) {
+  const long long n = static_cast<long long>(keys.size<integer_t>());
+  CHECK(data[1].size() == static_cast<size_t>(n) * num_col_ * sizeof(T));
+  // Rows of one request may repeat (the updates must then apply one after the other), so the
+  // parallel form is only taken when the ids are strictly increasing, i.e. provably distinct.
+  bool distinct = true;
+  for (long long i = 0; i < n; ++i) {
     const integer_t local = keys.As<integer_t>(i) - row_offset_;
     CHECK(local >= 0 && local < my_num_row_);
-    updater_->Update(static_cast<size_t>(num_col_), storage_.data(), vals + i * num_col_, &opt,
+    if (i > 0 && keys.As<integer_t>(i) <= keys.As<integer_t>(i - 1)) distinct = false;
+  }
+#pragma omp parallel for schedule(static) num_threads(distinct ? RowThreads(n) : 1)
+  for (long long i = 0; i < n; ++i) {
+    const integer_t local = keys.As<integer_t>(i) - row_offset_;
+    AddOption row_opt = opt;
+    updater_->Update(static_cast<size_t>(num_col_), storage_.data(), vals + i * num_col_, &row_opt,
                      static_cast<size_t>(local * num_col_));
   }
 }
@@ -272,9 +325,10 @@ void MatrixServerTable<T>::ProcessGet(const std::vector<Blob>& data, std::vector
     updater_->Access(storage_.size(), storage_.data(), reinterpret_cast<T*>(values.data()), 0, nullptr);
     result->push_back(std::move(values));
   } else {
-    const size_t n = keys.size<integer_t>();
-    Blob values(n * num_col_ * sizeof(T));
-    for (size_t i = 0; i < n; ++i) {
+    const long long n = static_cast<long long>(keys.size<integer_t>());
+    Blob values(static_cast<size_t>(n) * num_col_ * sizeof(T));
+#pragma omp parallel for schedule(static) num_threads(RowThreads(n))
+    for (long long i = 0; i < n; ++i) {
       const integer_t local = keys.As<integer_t>(i) - row_offset_;
       CHECK(local >= 0 && local < my_num_row_);
       updater_->Access(static_cast<size_t>(num_col_), storage_.data(),

@@ -6,6 +6,7 @@
 // scattered destination pointers / row-id array with one contiguous buffer.
 #ifndef MULTIVERSO_TABLE_MATRIX_TABLE_H_
 #define MULTIVERSO_TABLE_MATRIX_TABLE_H_
+#include <utility>
 #include <vector>
 #include "multiverso/table_interface.h"
 
@@ -78,9 +79,15 @@ class MatrixWorkerTable : public WorkerTable {
   virtual void FilterOutgoing(std::vector<Blob>* /*blobs*/) {}
   virtual int SubmitWholeAdd(T* data, size_t size, const AddOption* opt);
 
+  // Destination of one in-flight Get. Row requests keep (row id, destination) pairs sorted by
+  // row id -- built with one sort (none when the ids arrive sorted), looked up by binary search --
+  // instead of a node-per-row hash map: a WordEmbedding block pulls 10^5..10^6 rows per request.
   struct GetRecord {
     T* whole = nullptr;                              // destination of a whole-table Get
-    std::unordered_map<integer_t, T*> rows;          // row id -> destination
+    std::vector<std::pair<integer_t, T*>> rows;      // sorted by row id
+    void AddRow(integer_t row, T* dst) { rows.emplace_back(row, dst); }
+    void Seal();                                     // sort if needed
+    T* Find(integer_t row) const;
   };
   int SubmitGet(GetRecord&& rec, Blob keys, const GetOption* opt);
   integer_t num_row_, num_col_;
