@@ -57,6 +57,17 @@ int mvb_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 int mvb_stream_sync(void* stream);
 int mvb_host_alloc_pinned(int64_t bytes, void** out);
 int mvb_host_free_pinned(void* p);
+/* plain device memory, streams, events: for hosts without their own CUDA runtime (csrc/device_rt) */
+int mvb_device_malloc(int64_t bytes, void** out);
+int mvb_device_free(void* p);
+int mvb_device_sync(void);
+int mvb_stream_create(void** out);
+int mvb_stream_destroy(void* stream);
+int mvb_event_create(void** out, int timing);
+int mvb_event_record(void* event, void* stream);
+int mvb_event_sync(void* event);
+int mvb_event_elapsed_ms(void* start, void* stop, float* ms);
+int mvb_event_destroy(void* event);
 
 /* ---- signal pads / device barrier (K11) ------------------------------------
  * pads[r] = rank r's pad (uint64[MVB_PAD_WORDS]); slot(channel, src) on rank r is

@@ -107,6 +107,53 @@ extern "C" int mvb_host_free_pinned(void* p) {
   return 0;
 }
 
+// Plain device memory, streams and events for hosts that do not bring their own CUDA runtime
+// (the C++ device runtime, csrc/device_rt; the Python layer uses torch's allocator / streams).
+extern "C" int mvb_device_malloc(int64_t bytes, void** out) {
+  MVB_CUDA_CHECK(cudaMalloc(out, (size_t)(bytes > 0 ? bytes : 1)));
+  return 0;
+}
+extern "C" int mvb_device_free(void* p) {
+  MVB_CUDA_CHECK(cudaFree(p));
+  return 0;
+}
+extern "C" int mvb_device_sync(void) {
+  MVB_CUDA_CHECK(cudaDeviceSynchronize());
+  return 0;
+}
+extern "C" int mvb_stream_create(void** out) {
+  cudaStream_t s;
+  MVB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *out = s;
+  return 0;
+}
+extern "C" int mvb_stream_destroy(void* stream) {
+  MVB_CUDA_CHECK(cudaStreamDestroy((cudaStream_t)stream));
+  return 0;
+}
+extern "C" int mvb_event_create(void** out, int timing) {
+  cudaEvent_t e;
+  MVB_CUDA_CHECK(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+  *out = e;
+  return 0;
+}
+extern "C" int mvb_event_record(void* event, void* stream) {
+  MVB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int mvb_event_sync(void* event) {
+  MVB_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)event));
+  return 0;
+}
+extern "C" int mvb_event_elapsed_ms(void* start, void* stop, float* ms) {
+  MVB_CUDA_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+extern "C" int mvb_event_destroy(void* event) {
+  MVB_CUDA_CHECK(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // Signal pads. slot(channel, src) = pad[channel * MVB_MAX_RANKS + src].
 // ---------------------------------------------------------------------------

@@ -149,9 +149,41 @@ def build_host(verbose: bool = False) -> Path:
     return out
 
 
+def build_device_rt(verbose: bool = False) -> Path:
+    """Compile the native C++ device runtime (csrc/device_rt -> libmvdevice.so: C++ tables over
+    libmvb200.so + the host control plane of libmultiverso.so) and its tools under build/bin."""
+    cxx = _find("g++", "/usr/bin/g++")
+    out = LIBDIR / "libmvdevice.so"
+    srcdir = ROOT / "csrc" / "device_rt"
+    srcs = sorted(srcdir.glob("*.cpp"))
+    if cxx is None or not srcs:
+        return out
+    hdrs = sorted((ROOT / "include").rglob("*.h")) + [ROOT / "csrc" / "cuda" / "mvb200.h"]
+    inc = ["-I", str(ROOT / "include")]
+    deps = [LIBDIR / "libmultiverso.so", LIBDIR / "libmvb200.so"]
+    if _newer(srcs + hdrs + deps, out):
+        if verbose:
+            print("[build] g++ device_rt -> libmvdevice.so", flush=True)
+        _run([cxx, *CXX_FLAGS, *inc, "-shared", *map(str, srcs), "-o", str(out), f"-L{LIBDIR}", "-lmultiverso",
+              "-lmvb200", "-Wl,-rpath,$ORIGIN"], "link libmvdevice.so")
+    bindir = BUILD / "bin"
+    bindir.mkdir(parents=True, exist_ok=True)
+    tools = srcdir / "tools"
+    for appdir in sorted(p for p in tools.iterdir() if p.is_dir()) if tools.exists() else []:
+        asrcs = sorted(appdir.glob("*.cpp"))
+        exe = bindir / appdir.name
+        if asrcs and _newer(asrcs + hdrs + [out], exe):
+            if verbose:
+                print(f"[build] link {exe.name}", flush=True)
+            _run([cxx, *CXX_FLAGS, *inc, *map(str, asrcs), "-o", str(exe), f"-L{LIBDIR}", "-lmvdevice", "-lmultiverso",
+                  "-lmvb200", f"-Wl,-rpath,{LIBDIR}"], f"link {exe.name}")
+    return out
+
+
 def build_all(verbose: bool = False):
     build_host(verbose)
     build_cuda(verbose)
+    build_device_rt(verbose)
 
 
 if __name__ == "__main__":
