@@ -50,6 +50,22 @@ struct DeviceArray {
   T* ptr;
 };
 
+// A whole-table Add from every worker. BSP: the collective fused Add. Async: the one-sided pushes
+// of the ranks are serialised here (stateful updaters read-modify-write the owner's state
+// remotely, so concurrent pushes are not bit-reproducible -- by design, like the reference's
+// async server -- and the scenarios below want exact expectations).
+template <typename T>
+static void AddFromEveryWorker(dev::DenseTable<T>* table, const T* delta, const AddOption* opt) {
+  if (MV_CONFIG(sync) || dev::Size() == 1) {
+    table->Add(delta, opt);
+    return;
+  }
+  for (int r = 0; r < dev::Size(); ++r) {
+    if (dev::Rank() == r) table->Add(delta, opt);
+    dev::Barrier();
+  }
+}
+
 template <typename T>
 static void TestArray(int64_t size) {
   const int W = MV_NumWorkers();
@@ -194,8 +210,7 @@ static void TestUpdaters() {
     DeviceArray<float> d(n), out(n);
     d.Upload(delta);
     for (int step = 0; step < 2; ++step) {
-      table.Add(d.ptr, &opt);
-      if (!MV_CONFIG(sync)) dev::Barrier();
+      AddFromEveryWorker(&table, d.ptr, &opt);
       for (int w = 0; w < W; ++w)
         for (int64_t i = 0; i < n; ++i) {
           if (!strcmp(name, "sgd")) {
@@ -234,14 +249,15 @@ static void TestCheckpoint() {
   std::vector<float> delta(n, 0.25f);
   DeviceArray<float> d(n), a(n), b(n);
   d.Upload(delta);
-  table.Add(d.ptr, &opt);
+  AddFromEveryWorker(&table, d.ptr, &opt);
   dev::Barrier();
   const std::string path = "/tmp/mv_device_ckpt_" + std::to_string(dev::Rank()) + ".bin";
   {
     std::unique_ptr<Stream> s(StreamFactory::GetStream(URI(path), FileOpenMode::BinaryWrite));
     table.Store(s.get());
   }
-  table.Add(d.ptr, &opt);              // continue ...
+  dev::Barrier();                      // async pushes of the next step must not race with a peer's Store
+  AddFromEveryWorker(&table, d.ptr, &opt);   // continue ...
   dev::Barrier();
   table.Get(a.ptr);
   dev::Barrier();
@@ -250,7 +266,7 @@ static void TestCheckpoint() {
     table.Load(s.get());               // ... roll back shard + momentum state
   }
   dev::Barrier();
-  table.Add(d.ptr, &opt);              // the replayed step must reproduce the first continuation
+  AddFromEveryWorker(&table, d.ptr, &opt);   // the replayed step must reproduce the first continuation
   dev::Barrier();
   table.Get(b.ptr);
   EXPECT(a.Download() == b.Download());

@@ -62,7 +62,6 @@ def _find_symm(ptr: int, nbytes: int):
         if base <= ptr and ptr + nbytes <= base + cap:
             return buf, ptr - base
     return None, 0
-_symm_user: Dict[int, Tuple[object, int]] = {}       # local base ptr -> (buffer, nbytes) of symm_tensor() allocations
 
 
 def _aggregate_fused(rt, lib, st, data: torch.Tensor, nbytes: int) -> torch.Tensor:
