@@ -1,0 +1,113 @@
+"""CPU tests of the Python package's utilities and option plumbing: Dashboard / monitor
+(reference: include/multiverso/dashboard.h), Log levels / file tee / JSONL metrics
+(util/log.h), AddOption's 20-byte layout (updater/updater.h:13-69), MV_CreateTable over option
+structs, set_flag / flag errors, and the C-level dashboard of the host runtime."""
+import json
+import os
+import struct
+import sys
+import time
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+@pytest.fixture
+def mv_host():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("host-backend test (runs where there is no GPU)")
+    import multiverso_b200 as mv
+    mv.FLAGS.reset()
+    mv.init()
+    yield mv
+    mv.shutdown(finalize_net=False)
+    mv.FLAGS.reset()
+
+
+def test_dashboard_monitor_accumulates():
+    from multiverso_b200.utils import Dashboard
+    from multiverso_b200.utils.dashboard import monitor
+    Dashboard.reset()
+    for _ in range(3):
+        with monitor("UNIT_TEST_REGION"):
+            time.sleep(0.002)
+    snap = Dashboard.snapshot()
+    assert snap["UNIT_TEST_REGION"]["count"] == 3 and snap["UNIT_TEST_REGION"]["total_ms"] >= 5.0
+    assert "UNIT_TEST_REGION: count = 3" in Dashboard.watch("UNIT_TEST_REGION")
+    assert "not found" in Dashboard.watch("NO_SUCH_MONITOR")
+    Dashboard.reset()
+    assert Dashboard.snapshot() == {}
+
+
+def test_log_levels_file_and_metrics(tmp_path, capsys):
+    from multiverso_b200.utils import log as L
+    lg = L.Logger()
+    lg.rank = 3
+    lg.reset_log_file(str(tmp_path / "mv.log"))
+    lg.debug("hidden %d", 1)
+    lg.info("shown %d", 2)
+    lg.reset_log_level(L.DEBUG)
+    lg.debug("now shown")
+    with pytest.raises(L.FatalError):
+        lg.fatal("boom %s", "x")
+    out = capsys.readouterr().out
+    assert "hidden" not in out and "[INFO]" in out and "[rank 3] shown 2" in out and "[FATAL]" in out
+    text = (tmp_path / "mv.log").read_text()
+    assert "now shown" in text and "boom x" in text
+    lg.to_stderr = True
+    lg.error("to stderr")
+    assert "to stderr" in capsys.readouterr().err
+    lg.metric("ignored_before_open", 1)
+    lg.open_metrics(str(tmp_path / "m" / "metrics.jsonl"))
+    lg.metric("words_per_sec", 123.5, step=7)
+    rec = json.loads((tmp_path / "m" / "metrics.jsonl").read_text().splitlines()[0])
+    assert rec["name"] == "words_per_sec" and rec["value"] == 123.5 and rec["step"] == 7 and rec["rank"] == 3
+
+
+def test_add_option_wire_layout():
+    from multiverso_b200.tables.options import AddOption, GetOption
+    o = AddOption(worker_id=2, momentum=0.5, learning_rate=0.25, rho=0.125, lambda_=2.0)
+    raw = o.pack()
+    assert len(raw) == 20 and struct.unpack("<iffff", raw) == (2, 0.5, 0.25, 0.125, 2.0)
+    back = AddOption.unpack(raw)
+    assert (back.worker_id, back.momentum, back.learning_rate, back.rho, back.lambda_) == (2, 0.5, 0.25, 0.125, 2.0)
+    d = AddOption(worker_id=0)
+    assert (d.momentum, round(d.learning_rate, 6), round(d.rho, 6), round(d.lambda_, 6)) == (0.0, 0.01, 0.1, 0.1)
+    assert GetOption(worker_id=5).pack() == struct.pack("<i", 5)
+
+
+def test_create_table_from_options(mv_host):
+    mv = mv_host
+    a = mv.create_table(mv.ArrayTableOption(17, "float64"))
+    a.add(np.arange(17, dtype=np.float64))
+    assert np.array_equal(a.get(), np.arange(17, dtype=np.float64))
+    m = mv.create_table(mv.MatrixTableOption(5, 3, "float32", min_value=-0.5, max_value=0.5))
+    w = m.get().reshape(5, 3)
+    assert w.min() >= -0.5 and w.max() <= 0.5 and np.abs(w).sum() > 0      # server-side random init
+    s = mv.create_table(mv.MatrixOption(6, 2, "float32", is_sparse=True))
+    s.add_rows([1, 4], np.ones((2, 2), np.float32))
+    assert np.array_equal(s.get().reshape(6, 2)[[1, 4]], np.ones((2, 2), np.float32))
+    kv = mv.create_table(mv.KVTableOption("int64", "float32"))
+    kv.add([7], [1.5])
+    assert np.allclose(kv.get([7]), [1.5])
+    with pytest.raises(TypeError):
+        mv.create_table(object())
+
+
+def test_set_flag_and_identity(mv_host):
+    mv = mv_host
+    assert mv.rank() == 0 and mv.size() == 1 and mv.num_workers() == 1 and mv.num_servers() == 1
+    assert mv.worker_id() == 0 and mv.server_id() == 0 and mv.is_master_worker()
+    assert mv.worker_id_to_rank(0) == 0 and mv.server_id_to_rank(0) == 0
+    mv.set_flag("omp_threads", 2)
+    assert mv.FLAGS.get("omp_threads") == 2
+    with pytest.raises(KeyError):
+        mv.set_flag("definitely_not_a_flag", 1)
+    x = np.arange(6, dtype=np.float32)
+    mv.aggregate(x)                                   # world size 1: identity
+    assert np.array_equal(x, np.arange(6, dtype=np.float32))
+    mv.dashboard_display()                            # native Dashboard::Display must not raise
