@@ -107,5 +107,41 @@ def net_finalize() -> None:
     host.net_finalize()
 
 
+def save_table(table, uri: str) -> bool:
+    """MV_SaveTable: every server writes its shard of ``table`` (and the updater state) to
+    ``<uri>.shard<server_id>``; collective, ends with a barrier.  Same naming and byte layout
+    (raw shard dump, then the state slabs) on both backends."""
+    rt = _rt()
+    if rt.backend == "host":
+        return bool(table.store(uri))
+    ok = True
+    if rt.server_id() >= 0:
+        try:
+            with open(f"{uri}.shard{rt.server_id()}", "wb") as f:
+                table.store(f)
+        except OSError as e:
+            Log.error("save_table: %s", e)
+            ok = False
+    rt.barrier()
+    return ok
+
+
+def load_table(table, uri: str) -> bool:
+    """MV_LoadTable: the inverse of ``save_table`` (same number of servers)."""
+    rt = _rt()
+    if rt.backend == "host":
+        return bool(table.load(uri))
+    ok = True
+    if rt.server_id() >= 0:
+        try:
+            with open(f"{uri}.shard{rt.server_id()}", "rb") as f:
+                table.load(f)
+        except OSError as e:
+            Log.error("load_table: %s", e)
+            ok = False
+    rt.barrier()
+    return ok
+
+
 def dashboard_display() -> None:
     Dashboard.display()

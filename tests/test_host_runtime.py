@@ -115,3 +115,20 @@ def test_machine_file_bootstrap(tmp_path):
     port = random.randint(20000, 50000)
     out = run_mp(3, BIN, "array", f"-machine_file={mf}", f"-port={port}")
     assert out.count("PASS") == 3
+
+
+def test_cpp_examples_compile_and_run(tmp_path):
+    """examples/cpp/host_tables.cpp is the documented minimal C++ program: build it against the
+    in-tree library and run it on 3 ranks, BSP + sgd; device_tables.cpp must at least compile and
+    link against libmvdevice (it needs GPUs to run)."""
+    lib = os.path.join(ROOT, "multiverso_b200", "_lib")
+    exe = str(tmp_path / "host_tables")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "cpp", "host_tables.cpp"), "-o", exe, f"-L{lib}", "-lmultiverso",
+                    f"-Wl,-rpath,{lib}", "-pthread", "-fopenmp"], check=True)
+    out = run_mp(3, exe, "-sync=true", "-updater_type=sgd")
+    assert out.count("w[0] = -1.5, emb[42][0] = -3, counter = 3003") == 3, out
+    if os.path.exists(os.path.join(lib, "libmvdevice.so")):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "cpp", "device_tables.cpp"), "-o", str(tmp_path / "device_tables"),
+                        f"-L{lib}", "-lmvdevice", "-lmultiverso", "-lmvb200", f"-Wl,-rpath,{lib}"], check=True)

@@ -101,6 +101,12 @@ def test_checkpoint_roundtrip_host(mv_host, tmp_path):
     t.add(np.ones(100, np.float32))
     assert t.load(str(tmp_path / "ckpt"))
     assert np.array_equal(t.get(), np.arange(100, dtype=np.float32))
+    # the backend-independent spelling
+    assert mv.save_table(t, str(tmp_path / "ckpt2")) and os.path.exists(tmp_path / "ckpt2.shard0")
+    t.add(np.ones(100, np.float32))
+    assert mv.load_table(t, str(tmp_path / "ckpt2"))
+    assert np.array_equal(t.get(), np.arange(100, dtype=np.float32))
+    assert not mv.load_table(t, str(tmp_path / "no_such_checkpoint"))
 
 
 def test_multiprocess_python_api():
