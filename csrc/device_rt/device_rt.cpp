@@ -700,6 +700,17 @@ void MatrixTable<T>::AddRows(const int64_t* ids, int64_t k, const T* vals, const
   this->Wait(AddRowsAsync(ids, k, vals, option, stream));
 }
 
+template <typename T>
+int MatrixTable<T>::AddRowsDeltaAsync(const int64_t* ids, int64_t k, const float* cur, const float* old, int64_t ld,
+                                      float scale, CudaStream stream) {
+  auto& m = TableAccess::Of<T>(*this);
+  if (!std::is_same<T, float>::value || m.upd->n_states != 0)
+    Log::Fatal("AddRowsDelta needs an fp32 table with the default or sgd updater\n");
+  const float sign = m.upd->code == MVB_UPD_SGD ? -1.0f : 1.0f;
+  MVB_CHECK(mvb_add_rows_delta(&rows_->map, ids, k, cur, old, ld > 0 ? ld : this->num_col_, sign * scale, stream));
+  return this->Record(stream);
+}
+
 // --------------------------------------------------------------------------------- KVTable
 template <typename V>
 struct KVTable<V>::Impl {

@@ -56,6 +56,7 @@ struct DataBlock {
   std::vector<int32_t> in_slot;          // per token: slot in `input` (-1 at separators)
   std::vector<int32_t> out_slot;         // per token: slot in `output` (negative sampling)
   std::vector<int32_t> negative_pool;    // the block's negative samples, as slots of `output`
+  std::vector<int32_t> negative_pool_ids;   // the same draws as word ids (the GPU kernel maps ids itself)
   // hierarchical softmax: per input slot the Huffman path as slots of `output` + branch codes
   std::vector<int32_t> path_begin;       // input.size() + 1
   std::vector<int32_t> path_slot;

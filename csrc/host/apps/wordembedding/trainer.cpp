@@ -98,6 +98,7 @@ void Trainer::Prepare(DataBlock* b, uint64_t seed) const {
 
   std::vector<integer_t> out_ids;
   b->negative_pool.clear();
+  b->negative_pool_ids.clear();
   b->path_begin.clear();
   b->path_slot.clear();
   b->path_code.clear();
@@ -145,6 +146,7 @@ void Trainer::Prepare(DataBlock* b, uint64_t seed) const {
     for (size_t i = 0; i < b->tokens.size(); ++i) b->out_slot[i] = b->tokens[i] >= 0 ? slot[b->tokens[i]] : -1;
     b->negative_pool.resize(pool_ids.size());
     for (size_t i = 0; i < pool_ids.size(); ++i) b->negative_pool[i] = slot[pool_ids[i]];
+    b->negative_pool_ids = std::move(pool_ids);
   }
   b->output.ids = std::move(out_ids);
 }

@@ -181,6 +181,11 @@ class MatrixTable : public DenseTable<T> {
                CudaStream stream = nullptr);
   int AddRowsAsync(const int64_t* device_row_ids, int64_t k, const T* device_vals, const AddOption* option = nullptr,
                    CudaStream stream = nullptr);
+  // Fused AddDeltaParameter of the block protocol: rows[id] += (cur - old) * scale, pushed one-sided
+  // into the owners without materialising the delta. fp32 tables with a stateless updater
+  // (default / sgd: the sign follows the updater), num_col and ld multiples of 4.
+  int AddRowsDeltaAsync(const int64_t* device_row_ids, int64_t k, const float* device_cur, const float* device_old,
+                        int64_t ld, float scale, CudaStream stream = nullptr);
 
  private:
   struct Rows;

@@ -168,15 +168,28 @@ def build_device_rt(verbose: bool = False) -> Path:
               "-lmvb200", "-Wl,-rpath,$ORIGIN"], "link libmvdevice.so")
     bindir = BUILD / "bin"
     bindir.mkdir(parents=True, exist_ok=True)
-    tools = srcdir / "tools"
-    for appdir in sorted(p for p in tools.iterdir() if p.is_dir()) if tools.exists() else []:
+    # executables: csrc/device_rt/{tools,apps}/<name>/*.cpp -> build/bin/<name>; an optional SOURCES
+    # file lists extra repository sources and -I include directories shared with the CPU applications
+    appdirs = [p for group in ("tools", "apps") if (srcdir / group).exists()
+               for p in sorted((srcdir / group).iterdir()) if p.is_dir()]
+    for appdir in appdirs:
         asrcs = sorted(appdir.glob("*.cpp"))
+        extra_inc = []
+        listing = appdir / "SOURCES"
+        if listing.exists():
+            for line in listing.read_text().splitlines():
+                line = line.split("#", 1)[0].strip()
+                if line.startswith("-I"):
+                    extra_inc += ["-I", str(ROOT / line[2:])]
+                elif line:
+                    asrcs.append(ROOT / line)
         exe = bindir / appdir.name
-        if asrcs and _newer(asrcs + hdrs + [out], exe):
+        app_hdrs = hdrs + sorted((srcdir.parent / "host" / "apps").rglob("*.h"))
+        if asrcs and _newer(asrcs + app_hdrs + [out], exe):
             if verbose:
                 print(f"[build] link {exe.name}", flush=True)
-            _run([cxx, *CXX_FLAGS, *inc, *map(str, asrcs), "-o", str(exe), f"-L{LIBDIR}", "-lmvdevice", "-lmultiverso",
-                  "-lmvb200", f"-Wl,-rpath,{LIBDIR}"], f"link {exe.name}")
+            _run([cxx, *CXX_FLAGS, *inc, *extra_inc, *map(str, asrcs), "-o", str(exe), f"-L{LIBDIR}", "-lmvdevice",
+                  "-lmultiverso", "-lmvb200", f"-Wl,-rpath,{LIBDIR}"], f"link {exe.name}")
     return out
 
 

@@ -88,6 +88,22 @@ tma_debug)
 ncu_tma)
   MVB_SGNS_VARIANT=10 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgns_tma -s 3 -c 1 -f -o gpurun_out/sgns_tma python bench.py --steps 2 --warmup 3 --no-table-bw > gpurun_out/ncu_sgns_tma.log 2>&1; echo "ncu_tma rc=$?"; tail -2 gpurun_out/ncu_sgns_tma.log
   ;;
+devrt)
+  # native C++ device runtime scenarios (BSP + async) and the native GPU wordembedding application
+  if [ "$NG" -gt 1 ]; then L="python tools/mvrun.py -n $NG --timeout 200 --"; else L=""; fi
+  for sync in true false; do
+    timeout 260 $L build/bin/mv_device_test all -sync=$sync > gpurun_out/devrt_n${NG}_sync_$sync.log 2>&1; echo "mv_device_test sync=$sync rc=$?"; grep -E "PASS|FAIL|EXPECT" gpurun_out/devrt_n${NG}_sync_$sync.log | head -12
+  done
+  python - <<'PY'
+import numpy as np
+rng = np.random.default_rng(0)
+with open("gpurun_out/topics.txt", "w") as f:
+    for _ in range(20000):
+        t = rng.integers(20); ws = rng.integers(50, size=rng.integers(5, 20))
+        f.write(" ".join(f"t{t}w{w}" for w in ws) + "\n")
+PY
+  timeout 300 $L build/bin/wordembedding_gpu -train_file gpurun_out/topics.txt -output gpurun_out/topics_vec.txt -size 32 -cbow 0 -negative 5 -epoch 3 -min_count 1 -data_block_size 300000 > gpurun_out/we_gpu_n$NG.log 2>&1; echo "wordembedding_gpu rc=$?"; grep '^{' gpurun_out/we_gpu_n$NG.log | head -8 | cut -c1-400
+  ;;
 probe)
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+2)) tools/probe_symm.py > gpurun_out/probe.log 2>&1; echo "probe rc=$?"; tail -20 gpurun_out/probe.log
   ;;
