@@ -180,6 +180,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:
         args.gpus = world
+    if not torch.cuda.is_available():
+        # the headline benchmark is a B200 measurement; say so instead of a CUDA traceback
+        # (bench/cpu_apps.py measures the CPU plumbing mode)
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"metric": "wordembedding_words_per_sec", "value": None, "n_gpus": args.gpus,
+                              "unavailable": "no CUDA device in this process; run on a B200"}), flush=True)
+        return
     mv.init()
     rank = mv.rank()
     dev = torch.device("cuda", torch.cuda.current_device())
