@@ -9,8 +9,8 @@ ROOT=$(cd "$HERE/../.." && pwd)
 python "$HERE/convert.py" "${1:-.}"
 N=${2:-1}
 if [ "$N" -gt 1 ]; then
-  sed 's/^use_ps=false/use_ps=true/' "$HERE/mnist.config" > mnist_ps.config
+  sed 's/^use_ps            = false/use_ps            = true/' "$HERE/mnist_softmax.config" > mnist_ps.config
   python "$ROOT/tools/mvrun.py" -n "$N" -- "$ROOT/build/bin/logreg" mnist_ps.config
 else
-  "$ROOT/build/bin/logreg" "$HERE/mnist.config"
+  "$ROOT/build/bin/logreg" "$HERE/mnist_softmax.config"
 fi

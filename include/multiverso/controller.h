@@ -1,5 +1,7 @@
-// Controller actor (rank 0 only): node registration -> dense worker/server ids, and the
-// global barrier (src/controller.cpp:12-102).
+// Controller actor (rank 0 only): the two rendezvous of the control plane. Registration gathers
+// one Node per rank, hands out dense worker / server ids in rank order and broadcasts the table;
+// the barrier gathers one message per rank and releases everybody (reference behaviour:
+// src/controller.cpp:12-102).
 #ifndef MULTIVERSO_CONTROLLER_H_
 #define MULTIVERSO_CONTROLLER_H_
 #include <vector>
@@ -12,11 +14,13 @@ class Controller : public Actor {
   Controller();
 
  private:
-  void ProcessBarrier(MessagePtr& msg);
-  void ProcessRegister(MessagePtr& msg);
-  std::vector<MessagePtr> barrier_waiting_;
-  std::vector<MessagePtr> register_waiting_;
-  std::vector<Node> nodes_;
+  void OnBarrierArrival(MessagePtr& msg);
+  void OnRegistration(MessagePtr& msg);
+  // Reply to every parked request; this rank's own reply goes out last.
+  void ReleaseAll(std::vector<MessagePtr>* parked, const std::vector<Blob>& payload);
+  std::vector<MessagePtr> at_barrier_;
+  std::vector<MessagePtr> registering_;
+  std::vector<Node> roster_;
 };
 }  // namespace multiverso
 #endif
