@@ -1,4 +1,5 @@
 #include "multiverso/blob.h"
+#include "multiverso/util/parallel_for.h"
 #include "multiverso/util/allocator.h"
 
 namespace multiverso {
@@ -6,7 +7,7 @@ namespace multiverso {
 Blob::Blob(size_t size) : data_(size ? Allocator::Get()->Alloc(size) : nullptr), size_(size) {}
 Blob::Blob(const void* data, size_t size)
     : data_(size ? Allocator::Get()->Alloc(size) : nullptr), size_(size) {
-  if (size) std::memcpy(data_, data, size);
+  if (size) ParallelMemcpy(data_, data, size);
 }
 Blob::Blob(const Blob& rhs) : data_(rhs.data_), size_(rhs.size_) {
   if (data_) Allocator::Get()->Refer(data_);

@@ -2,6 +2,7 @@
 #include "multiverso/table/array_table.h"
 #include "multiverso/multiverso.h"
 #include "multiverso/util/log.h"
+#include "multiverso/util/parallel_for.h"
 
 namespace multiverso {
 
@@ -89,7 +90,7 @@ void ArrayWorker<T>::ProcessReplyGet(std::vector<Blob>& reply, int msg_id) {
     dst = dest_.at(msg_id);
   }
   CHECK(reply[1].size() == (offsets_[sid + 1] - offsets_[sid]) * sizeof(T));
-  std::memcpy(dst + offsets_[sid], reply[1].data(), reply[1].size());
+  ParallelMemcpy(dst + offsets_[sid], reply[1].data(), reply[1].size());
 }
 
 template <typename T>

@@ -3,10 +3,14 @@
 #include "multiverso/table/matrix.h"
 #include "multiverso/multiverso.h"
 #include "multiverso/table/sparse_matrix_table.h"
+#include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
+#include "multiverso/util/parallel_for.h"
 #include "multiverso/util/quantization_util.h"
 
 namespace multiverso {
+
+MV_DECLARE_int(omp_threads);
 
 namespace {
 const integer_t kWholeTable = -1;
@@ -38,8 +42,11 @@ int MatrixWorker<T>::SubmitWholeAdd(T* data, size_t size, const AddOption* opt) 
     return id;
   }
   Blob vals(rows.size() * C * sizeof(T));
-  for (size_t i = 0; i < rows.size(); ++i)
-    std::memcpy(vals.data() + i * C * sizeof(T), data + rows[i] * C, C * sizeof(T));
+  ParallelFor(static_cast<int64_t>(rows.size()), rows.size() >= 2048 ? std::max(1, MV_CONFIG(omp_threads)) : 1,
+              [&](int64_t lo, int64_t hi) {
+                for (int64_t i = lo; i < hi; ++i)
+                  std::memcpy(vals.data() + i * C * sizeof(T), data + rows[i] * C, C * sizeof(T));
+              });
   return WorkerTable::AddAsync(Blob(rows.data(), rows.size() * sizeof(integer_t)), std::move(vals), opt);
 }
 
@@ -110,21 +117,26 @@ void MatrixServer<T>::ProcessGet(const std::vector<Blob>& data, std::vector<Blob
     MatrixServerTable<T>::ProcessGet(data, result);
     return;
   }
-  std::vector<integer_t> rows;
+  // collect this worker's stale rows (and mark them fresh), then gather them in parallel
   auto& mine = stale_[worker];
-  for (integer_t r = 0; r < this->my_num_row_; ++r)
+  size_t n_stale = 0;
+  for (unsigned char f : mine) n_stale += f;
+  Blob ids(n_stale * sizeof(integer_t));
+  size_t k = 0;
+  for (integer_t r = 0; r < this->my_num_row_ && k < n_stale; ++r)
     if (mine[static_cast<size_t>(r)]) {
-      rows.push_back(r + this->row_offset_);
+      ids.As<integer_t>(k++) = r + this->row_offset_;
       mine[static_cast<size_t>(r)] = 0;
     }
-  const size_t C = static_cast<size_t>(this->num_col_);
-  Blob ids(rows.size() * sizeof(integer_t));
-  Blob vals(rows.size() * C * sizeof(T));
-  for (size_t i = 0; i < rows.size(); ++i) {
-    ids.As<integer_t>(i) = rows[i];
-    std::memcpy(vals.data() + i * C * sizeof(T),
-                this->storage_.data() + static_cast<size_t>(rows[i] - this->row_offset_) * C, C * sizeof(T));
-  }
+  const size_t row_bytes = static_cast<size_t>(this->num_col_) * sizeof(T);
+  Blob vals(n_stale * row_bytes);
+  const char* base = reinterpret_cast<const char*>(this->storage_.data());
+  ParallelFor(static_cast<int64_t>(n_stale), n_stale >= 2048 ? std::max(1, MV_CONFIG(omp_threads)) : 1,
+              [&](int64_t lo, int64_t hi) {
+                for (int64_t i = lo; i < hi; ++i)
+                  std::memcpy(vals.data() + i * row_bytes,
+                              base + static_cast<size_t>(ids.As<integer_t>(i) - this->row_offset_) * row_bytes, row_bytes);
+              });
   // an explicit (possibly empty) row list -- no row-0 placeholder
   result->push_back(std::move(ids));
   result->push_back(std::move(vals));

@@ -5,6 +5,7 @@
 #include "multiverso/multiverso.h"
 #include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
+#include "multiverso/util/parallel_for.h"
 
 namespace multiverso {
 
@@ -13,8 +14,9 @@ MV_DECLARE_int(omp_threads);
 namespace {
 const integer_t kWholeTable = -1;
 inline bool IsWhole(const Blob& keys) { return keys.size<integer_t>() == 1 && keys.As<integer_t>(0) == kWholeTable; }
-// Row loops (gather / scatter / per-row update) go parallel above this many rows; they are
-// random accesses over the shard, so extra threads buy memory-level parallelism.
+// Row loops (gather / scatter / per-row update) go parallel above this many rows (ParallelFor,
+// `-omp_threads` wide); they are random accesses over the shard, so extra threads buy
+// memory-level parallelism.
 constexpr long long kParallelRows = 2048;
 inline int RowThreads(long long rows) { return rows >= kParallelRows ? std::max(1, MV_CONFIG(omp_threads)) : 1; }
 }  // namespace
@@ -138,9 +140,10 @@ int MatrixWorkerTable<T>::AddAsync(const std::vector<integer_t>& row_ids, const 
   CHECK(size == static_cast<size_t>(num_col_) && row_ids.size() == data_vec.size());
   Blob vals(row_ids.size() * num_col_ * sizeof(T));
   const long long rows = static_cast<long long>(row_ids.size());
-#pragma omp parallel for schedule(static) num_threads(RowThreads(rows))
-  for (long long i = 0; i < rows; ++i)
-    std::memcpy(vals.data() + i * num_col_ * sizeof(T), data_vec[i], num_col_ * sizeof(T));
+  const size_t row_bytes = static_cast<size_t>(num_col_) * sizeof(T);
+  ParallelFor(rows, RowThreads(rows), [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) std::memcpy(vals.data() + i * row_bytes, data_vec[i], row_bytes);
+  });
   return WorkerTable::AddAsync(Blob(row_ids.data(), row_ids.size() * sizeof(integer_t)), std::move(vals), opt);
 }
 template <typename T>
@@ -202,9 +205,10 @@ int MatrixWorkerTable<T>::Partition(const std::vector<Blob>& kv, MsgType type,
         v.push_back(std::move(ids));
         if (is_add) {
           Blob vals(b.size() * row_bytes);
-#pragma omp parallel for schedule(static) num_threads(RowThreads(rows))
-          for (long long j = 0; j < rows; ++j)
-            std::memcpy(vals.data() + j * row_bytes, kv[1].data() + b[j] * row_bytes, row_bytes);
+          ParallelFor(rows, RowThreads(rows), [&](int64_t lo, int64_t hi) {
+            for (int64_t j = lo; j < hi; ++j)
+              std::memcpy(vals.data() + j * row_bytes, kv[1].data() + b[j] * row_bytes, row_bytes);
+          });
           v.push_back(std::move(vals));
         }
         if (option) v.push_back(*option);
@@ -226,18 +230,19 @@ void MatrixWorkerTable<T>::ProcessReplyGet(std::vector<Blob>& reply, int msg_id)
   GetRecord& rec = records_.at(msg_id);
   if (IsWhole(keys)) {
     CHECK(rec.whole != nullptr);
-    std::memcpy(rec.whole + part_.row_begin[sid] * num_col_, reply[1].data(), reply[1].size());
+    ParallelMemcpy(rec.whole + part_.row_begin[sid] * num_col_, reply[1].data(), reply[1].size());
     return;
   }
   const long long n = static_cast<long long>(keys.size<integer_t>());
   CHECK(reply[1].size() == static_cast<size_t>(n) * row_bytes);
-#pragma omp parallel for schedule(static) num_threads(RowThreads(n))
-  for (long long i = 0; i < n; ++i) {
-    const integer_t r = keys.As<integer_t>(i);
-    T* dst = rec.Find(r);
-    if (dst == nullptr && rec.whole) dst = rec.whole + r * num_col_;   // sparse delta-pull into the whole buffer
-    if (dst) std::memcpy(dst, reply[1].data() + i * row_bytes, row_bytes);
-  }
+  ParallelFor(n, RowThreads(n), [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      const integer_t r = keys.As<integer_t>(i);
+      T* dst = rec.Find(r);
+      if (dst == nullptr && rec.whole) dst = rec.whole + r * num_col_;   // sparse delta-pull into the whole buffer
+      if (dst) std::memcpy(dst, reply[1].data() + i * row_bytes, row_bytes);
+    }
+  });
 }
 
 template <typename T>
@@ -306,13 +311,14 @@ void MatrixServerTable<T>::ProcessAdd(const std::vector<Blob>& data) {
     CHECK(local >= 0 && local < my_num_row_);
     if (i > 0 && keys.As<integer_t>(i) <= keys.As<integer_t>(i - 1)) distinct = false;
   }
-#pragma omp parallel for schedule(static) num_threads(distinct ? RowThreads(n) : 1)
-  for (long long i = 0; i < n; ++i) {
-    const integer_t local = keys.As<integer_t>(i) - row_offset_;
+  ParallelFor(n, distinct ? RowThreads(n) : 1, [&](int64_t lo, int64_t hi) {
     AddOption row_opt = opt;
-    updater_->Update(static_cast<size_t>(num_col_), storage_.data(), vals + i * num_col_, &row_opt,
-                     static_cast<size_t>(local * num_col_));
-  }
+    for (int64_t i = lo; i < hi; ++i) {
+      const integer_t local = keys.As<integer_t>(i) - row_offset_;
+      updater_->Update(static_cast<size_t>(num_col_), storage_.data(), vals + i * num_col_, &row_opt,
+                       static_cast<size_t>(local * num_col_));
+    }
+  });
 }
 
 template <typename T>
@@ -327,14 +333,15 @@ void MatrixServerTable<T>::ProcessGet(const std::vector<Blob>& data, std::vector
   } else {
     const long long n = static_cast<long long>(keys.size<integer_t>());
     Blob values(static_cast<size_t>(n) * num_col_ * sizeof(T));
-#pragma omp parallel for schedule(static) num_threads(RowThreads(n))
-    for (long long i = 0; i < n; ++i) {
-      const integer_t local = keys.As<integer_t>(i) - row_offset_;
-      CHECK(local >= 0 && local < my_num_row_);
-      updater_->Access(static_cast<size_t>(num_col_), storage_.data(),
-                       reinterpret_cast<T*>(values.data()) + i * num_col_,
-                       static_cast<size_t>(local * num_col_), nullptr);
-    }
+    ParallelFor(n, RowThreads(n), [&](int64_t lo, int64_t hi) {
+      for (int64_t i = lo; i < hi; ++i) {
+        const integer_t local = keys.As<integer_t>(i) - row_offset_;
+        CHECK(local >= 0 && local < my_num_row_);
+        updater_->Access(static_cast<size_t>(num_col_), storage_.data(),
+                         reinterpret_cast<T*>(values.data()) + i * num_col_,
+                         static_cast<size_t>(local * num_col_), nullptr);
+      }
+    });
     result->push_back(std::move(values));
   }
   result->emplace_back(&server_id_, sizeof(int));

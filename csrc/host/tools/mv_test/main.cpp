@@ -374,8 +374,9 @@ static void TestMatrixPerf(bool sparse, int num_row) {
   const size_t size = static_cast<size_t>(num_row) * C;
   std::vector<float> data(size), delta(size);
   for (size_t i = 0; i < size; ++i) delta[i] = static_cast<float>(i % 100003);
-  Timer timer;
+  Timer timer, turn_timer;
   for (int percent = 0; percent < 10; ++percent) {
+    turn_timer.Start();
     MatrixWorkerTable<float>* t;
     if (sparse) {
       MatrixOption<float> o;
@@ -386,6 +387,7 @@ static void TestMatrixPerf(bool sparse, int num_row) {
     }
     if (!t) continue;                       // server-only rank
     MV_Barrier();
+    if (me == 0 && getenv("MV_TEST_TIMING")) printf("    [table created after %.1f ms]\n", turn_timer.elapse());
     GetOption gopt;
     gopt.set_worker_id(me);
     timer.Start();
@@ -398,6 +400,7 @@ static void TestMatrixPerf(bool sparse, int num_row) {
       if (i % 10 <= percent && i % W == me) { ids.push_back(i); ptrs.push_back(delta.data() + static_cast<size_t>(i) * C); }
     AddOption aopt;
     aopt.set_worker_id(me);
+    if (me == 0 && getenv("MV_TEST_TIMING")) printf("    [ids built after %.1f ms]\n", turn_timer.elapse());
     timer.Start();
     if (!ids.empty()) t->Add(ids, ptrs, C, &aopt);
     const double add_ms = timer.elapse();
@@ -405,6 +408,7 @@ static void TestMatrixPerf(bool sparse, int num_row) {
     timer.Start();
     t->Get(data.data(), size, &gopt);
     const double get_ms = timer.elapse();
+    timer.Start();
     bool ok = true;
     for (int i = 0; i < num_row && ok; ++i)
       for (int c = 0; c < C; ++c) {
@@ -412,12 +416,14 @@ static void TestMatrixPerf(bool sparse, int num_row) {
         if (data[static_cast<size_t>(i) * C + c] != expect) { ok = false; break; }
       }
     EXPECT(ok);
+    if (me == 0 && getenv("MV_TEST_TIMING")) printf("    [verify %.1f ms, since turn start %.1f ms]\n", timer.elapse(), turn_timer.elapse());
     if (me == 0)
-      printf("  %s %d x %d, add %d0%% of the rows: first get %.1f ms, add %.1f ms (%zu rows), get %.1f ms (%.2f GB/s)\n",
+      printf("  %s %d x %d, add %d0%% of the rows: first get %.1f ms, add %.1f ms (%zu rows), get %.1f ms (%.2f GB/s)",
              sparse ? "sparse" : "dense", num_row, C, percent + 1, first_ms, add_ms, ids.size(), get_ms,
              size * sizeof(float) / get_ms / 1e6);
     MV_Barrier();
     delete t;
+    if (me == 0) printf(", turn %.1f ms\n", turn_timer.elapse());   // table creation .. verification .. teardown
   }
   if (me == 0) Dashboard::Display();
   MV_ShutDown();

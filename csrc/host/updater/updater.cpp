@@ -9,6 +9,7 @@
 #include "multiverso/updater/sgd_updater.h"
 #include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
+#include "multiverso/util/parallel_for.h"
 
 namespace multiverso {
 
@@ -19,13 +20,16 @@ template <typename T>
 void Updater<T>::Update(size_t num_element, T* data, T* delta, AddOption*, size_t offset) {
   T* d = data + offset;
   const long long n = static_cast<long long>(num_element);
-#pragma omp parallel for schedule(static) num_threads(MV_CONFIG(omp_threads)) if (n > 65536)
-  for (long long i = 0; i < n; ++i) d[i] += delta[i];
+  // `-omp_threads` keeps its meaning (width of the default updater on large shards); row-sized
+  // updates (one call per row of a MatrixTable) run inline
+  ParallelFor(n, n > 65536 ? MV_CONFIG(omp_threads) : 1, [d, delta](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) d[i] += delta[i];
+  });
 }
 
 template <typename T>
 void Updater<T>::Access(size_t num_element, T* data, T* blob_data, size_t offset, AddOption*) {
-  std::memcpy(blob_data, data + offset, num_element * sizeof(T));
+  ParallelMemcpy(blob_data, data + offset, num_element * sizeof(T));
 }
 
 // Gradient-based updaters only make sense for floating-point tables.

@@ -25,5 +25,11 @@ g++ -O2 -std=c++11 -fPIC -I$ROOT/baseline/mpi_shim -c $ROOT/baseline/mpi_shim/mp
 pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
 g++ -fopenmp -o $OUT/bin/wordembedding $OBJ/*.o -lpthread -ldl
-rm -rf $OBJ
 echo "built $OUT/bin/wordembedding"
+# the reference's matrix perf test (Test/test_matrix_perf.cpp, unmodified) with a tiny driver
+g++ $CXXFLAGS -c $REF/Test/test_matrix_perf.cpp -o $OBJ/perf_test.o &
+g++ -O2 -std=c++11 -c $ROOT/baseline/ref_matrix_perf_main.cpp -o $OBJ/perf_main.o &
+wait
+g++ -fopenmp -o $OUT/bin/matrix_perf $OBJ/core_*.o $OBJ/mpi_shim.o $OBJ/perf_test.o $OBJ/perf_main.o -lpthread -ldl \
+  && echo "built $OUT/bin/matrix_perf"
+rm -rf $OBJ

@@ -26,7 +26,9 @@ def main():
     cmd = a.cmd[1:] if a.cmd and a.cmd[0] == "--" else a.cmd
     if not cmd:
         ap.error("no command")
-    port = a.port or random.randint(20000, 50000)
+    # below the kernel's ephemeral range (32768-60999): a rank's outgoing connection must never be
+    # handed the port another rank is about to listen on
+    port = a.port or random.randrange(10000, 30000, 16)
     procs = []
     for r in range(a.n):
         env = dict(os.environ, MV_RANK=str(r), MV_SIZE=str(a.n), MV_PORT=str(port),
