@@ -9,6 +9,9 @@
 //
 // Scenarios mirror Test/unittests/*.cpp and Test/test_*.cpp with their exact integer
 // expectations; exit code 0 = pass.
+#include <atomic>
+#include <thread>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +38,7 @@
 #include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
 #include "multiverso/util/mt_queue.h"
+#include "multiverso/util/parallel_for.h"
 #include "multiverso/util/quantization_util.h"
 #include "multiverso/util/waiter.h"
 
@@ -171,6 +175,46 @@ static void TestIOAndFilters() {
   EXPECT(oout[1].size<float>() == 5 && oout[1].As<float>(0) == 2.f && oout[1].As<float>(2) == -3.f);
 }
 
+// ParallelFor / ParallelMemcpy: every index exactly once, from several caller threads at once
+// (the caller, the worker actor and the server actor share the pool), odd sizes, big copies.
+static void TestParallelFor() {
+  EXPECT(ParallelForCapacity() >= 1);
+  for (int64_t n : {0, 1, 7, 1000, 100003}) {
+    std::vector<std::atomic<int>> hits(static_cast<size_t>(n));
+    for (auto& h : hits) h.store(0);
+    ParallelFor(n, 8, [&](int64_t lo, int64_t hi) {
+      for (int64_t i = lo; i < hi; ++i) hits[static_cast<size_t>(i)].fetch_add(1);
+    });
+    bool once = true;
+    for (auto& h : hits) once = once && h.load() == 1;
+    EXPECT(once);
+  }
+  std::vector<std::thread> callers;
+  std::atomic<int> bad{0};
+  for (int t = 0; t < 4; ++t)
+    callers.emplace_back([&bad, t] {
+      for (int rep = 0; rep < 20; ++rep) {
+        const int64_t n = 5000 + 37 * t + rep;
+        std::atomic<int64_t> sum{0};
+        ParallelFor(n, 4, [&](int64_t lo, int64_t hi) {
+          int64_t s = 0;
+          for (int64_t i = lo; i < hi; ++i) s += i;
+          sum.fetch_add(s);
+        });
+        if (sum.load() != n * (n - 1) / 2) bad.fetch_add(1);
+      }
+    });
+  for (auto& c : callers) c.join();
+  EXPECT(bad.load() == 0);
+  std::vector<char> src((24u << 20) + 12345), dst(src.size(), 0);
+  for (size_t i = 0; i < src.size(); ++i) src[i] = static_cast<char>(i * 131 + 7);
+  ParallelMemcpy(dst.data(), src.data(), src.size());
+  EXPECT(src == dst);
+  std::vector<char> small_dst(100, 0);
+  ParallelMemcpy(small_dst.data(), src.data(), small_dst.size());
+  EXPECT(std::equal(small_dst.begin(), small_dst.end(), src.begin()));
+}
+
 static void TestAllreduceSchedules() {
   // Bruck: total blocks received == size-1 for every rank / size
   for (int n = 1; n <= 9; ++n)
@@ -246,6 +290,7 @@ static int RunUnit() {
   TestBlobMessageNode();
   TestFlagsAllocatorQueue();
   TestIOAndFilters();
+  TestParallelFor();
   TestAllreduceSchedules();
   UnitWithRuntime(false);
   UnitWithRuntime(true);    // test_sync.cpp:25-43
