@@ -275,12 +275,15 @@ SymmBuffer::SymmBuffer(size_t bytes) : bytes_(std::max<size_t>(bytes, 16)), rank
   }
 }
 
+// Collective like the constructor. CUDA requires every importing process to close its mapping
+// before the exporting process frees the allocation, hence: unmap the peers' slabs, rendezvous on
+// the control plane, then free the local slab.
 SymmBuffer::~SymmBuffer() {
-  for (int r = 0; r < kMaxRanks; ++r) {
-    if (ptrs_[r] == nullptr) continue;
-    if (r == rank_) mvb_symm_free(ptrs_[r]);
-    else mvb_ipc_close_handle(ptrs_[r]);
-  }
+  Context& c = Ctx();
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (r != rank_ && ptrs_[r] != nullptr) mvb_ipc_close_handle(ptrs_[r]);
+  if (c.started && c.size > 1) MV_Barrier();
+  if (ptrs_[rank_] != nullptr) mvb_symm_free(ptrs_[rank_]);
 }
 
 // -------------------------------------------------------------------------------- AsyncOps

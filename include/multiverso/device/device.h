@@ -63,8 +63,8 @@ void CopyToDevice(void* dst_device, const void* src_host, size_t bytes, CudaStre
 void CopyToHost(void* dst_host, const void* src_device, size_t bytes, CudaStream stream = nullptr);
 void StreamSync(CudaStream stream = nullptr);
 
-// The same-sized slab on every rank, mapped into every process (collective constructor:
-// all ranks must create their SymmBuffers in the same order).
+// The same-sized slab on every rank, mapped into every process. Constructor and destructor are
+// collective: all ranks create and destroy their SymmBuffers in the same order.
 class SymmBuffer {
  public:
   explicit SymmBuffer(size_t bytes);
