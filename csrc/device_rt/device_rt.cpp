@@ -257,6 +257,23 @@ void CopyToHost(void* dst, const void* src, size_t bytes, CudaStream stream) {
 }
 void StreamSync(CudaStream stream) { MVB_CHECK(mvb_stream_sync(stream)); }
 
+EventTimer::EventTimer() : start_(nullptr), stop_(nullptr) {
+  MVB_CHECK(mvb_event_create(&start_, 1));
+  MVB_CHECK(mvb_event_create(&stop_, 1));
+}
+EventTimer::~EventTimer() {
+  mvb_event_destroy(start_);
+  mvb_event_destroy(stop_);
+}
+void EventTimer::Start(CudaStream stream) { MVB_CHECK(mvb_event_record(start_, stream)); }
+float EventTimer::StopMs(CudaStream stream) {
+  MVB_CHECK(mvb_event_record(stop_, stream));
+  MVB_CHECK(mvb_event_sync(stop_));
+  float ms = 0;
+  MVB_CHECK(mvb_event_elapsed_ms(start_, stop_, &ms));
+  return ms;
+}
+
 // ------------------------------------------------------------------------------ SymmBuffer
 SymmBuffer::SymmBuffer(size_t bytes) : bytes_(std::max<size_t>(bytes, 16)), rank_(Ctx().rank) {
   Context& c = Ctx();

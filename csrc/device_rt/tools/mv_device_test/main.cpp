@@ -274,9 +274,47 @@ static void TestCheckpoint() {
   dev::Barrier();
 }
 
+// Whole-table Add / Get of the BASELINE MatrixTable (1M x 512 fp32 unless `rows` is given), timed with
+// CUDA events after 3 warm-up rounds; the slowest rank's time is what counts (max over ranks: every
+// rank prints its own line). Same kernels as bench/matrix_bw.py, driven from C++.
+static void BenchMatrix(int64_t rows) {
+  const int64_t cols = 512;
+  dev::MatrixTable<float> table(rows, cols, dev::TableInit(), "sgd");
+  const size_t n = static_cast<size_t>(rows) * cols;
+  float* out = static_cast<float*>(dev::DeviceAlloc(n * sizeof(float)));
+  dev::EventTimer timer;
+  double add_ms = 0, get_ms = 0;
+  const int warmup = 3, iters = 10;
+  for (int i = 0; i < warmup + iters; ++i) {
+    float* delta = table.Staging();                 // zero-copy Add: the delta is produced in the staging buffer
+    dev::Barrier();
+    timer.Start();
+    table.Wait(table.AddStagedAsync());
+    const float a = timer.StopMs();
+    dev::Barrier();
+    timer.Start();
+    table.Get(out);
+    const float g = timer.StopMs();
+    if (i >= warmup) {
+      add_ms += a;
+      get_ms += g;
+    }
+    (void)delta;
+  }
+  add_ms /= iters;
+  get_ms /= iters;
+  const double gb = n * sizeof(float) / 1e9;
+  printf("{\"bench\": \"matrix_table\", \"rank\": %d, \"ranks\": %d, \"rows\": %lld, \"cols\": %lld, \"add_ms\": %.4f, "
+         "\"get_ms\": %.4f, \"add_gbs\": %.1f, \"get_gbs\": %.1f}\n",
+         dev::Rank(), dev::Size(), static_cast<long long>(rows), static_cast<long long>(cols), add_ms, get_ms,
+         gb / add_ms * 1e3, gb / get_ms * 1e3);
+  dev::Barrier();
+  dev::DeviceFree(out);
+}
+
 int main(int argc, char* argv[]) {
   if (argc < 2) {
-    fprintf(stderr, "usage: mv_device_test all|array|matrix|kv|aggregate|updaters|checkpoint [-flag=value ...]\n");
+    fprintf(stderr, "usage: mv_device_test all|array|matrix|kv|aggregate|updaters|checkpoint|bench [rows] [-flag=value ...]\n");
     return 2;
   }
   const std::string which = argv[1];
@@ -292,6 +330,7 @@ int main(int argc, char* argv[]) {
   if (all || which == "aggregate") TestAggregate();
   if (all || which == "updaters") TestUpdaters();
   if (all || which == "checkpoint") TestCheckpoint();
+  if (which == "bench") BenchMatrix(argc > 2 ? atoll(argv[2]) : 1000000);
   dev::Barrier();
   printf("[mv_device_test %s rank %d/%d gpu %d] %s\n", which.c_str(), dev::Rank(), dev::Size(), dev::DeviceId(),
          g_fail ? "FAIL" : "PASS");

@@ -62,6 +62,19 @@ void DeviceFree(void* p);
 void CopyToDevice(void* dst_device, const void* src_host, size_t bytes, CudaStream stream = nullptr);
 void CopyToHost(void* dst_host, const void* src_device, size_t bytes, CudaStream stream = nullptr);
 void StreamSync(CudaStream stream = nullptr);
+// Device-side timing for benchmarks: CUDA events on a stream (never wall clock).
+class EventTimer {
+ public:
+  EventTimer();
+  ~EventTimer();
+  void Start(CudaStream stream = nullptr);
+  // Records the stop event, waits for it and returns the elapsed milliseconds.
+  float StopMs(CudaStream stream = nullptr);
+
+ private:
+  void* start_;
+  void* stop_;
+};
 
 // The same-sized slab on every rank, mapped into every process. Constructor and destructor are
 // collective: all ranks create and destroy their SymmBuffers in the same order.
