@@ -137,7 +137,13 @@ class _HostTable:
     def table_id(self) -> int:
         return _lib().MV_TableId(self.handle) if self.handle.value else -1
 
-    def wait(self, handle=None) -> None:   # sync calls only through the C API
+    def wait(self, handle=None) -> None:
+        """Async handles of this backend are already complete (the C API waits for Gets; async Adds are
+        applied by the servers in order), kept so that scripts written for the device backend run here."""
+        return None
+
+    def finish_train(self) -> None:
+        """Server_Finish_Train is sent by MV_ShutDown on this backend."""
         return None
 
     def store(self, uri: str) -> bool:
@@ -179,6 +185,10 @@ class HostArrayTable(_HostTable):
     def add_async(self, data, option: Optional[AddOption] = None):
         self.add(data, option, sync=False)
         return 0
+
+    def get_async(self, out=None):
+        """(handle, buffer) like the device backend; the buffer is already filled."""
+        return 0, self.get(out)
 
 
 class HostMatrixTable(_HostTable):
@@ -240,6 +250,36 @@ class HostMatrixTable(_HostTable):
 
     def add_row(self, row_id: int, values, option: Optional[AddOption] = None) -> None:
         self.add_rows([row_id], values, option)
+
+    # the *_async spellings of the device backend (same return shapes)
+    def add_async(self, data, option: Optional[AddOption] = None):
+        self.add(data, option, sync=False)
+        return 0
+
+    def add_rows_async(self, row_ids, values, option: Optional[AddOption] = None):
+        self.add_rows(row_ids, values, option, sync=False)
+        return 0
+
+    def get_async(self, out=None, option: Optional[GetOption] = None):
+        return 0, self.get(out, option)
+
+    def get_rows_async(self, row_ids, out=None):
+        return 0, self.get_rows(row_ids, out)
+
+    def get_stale(self, option: Optional[GetOption] = None):
+        """Delta pull of a sparse table: (row_ids, rows) that changed since this worker's previous
+        pull (explicit empty result when nothing changed).  The servers return only the stale rows and
+        the C API scatters them into the caller's buffer, so the table keeps that buffer between pulls
+        and reports the rows whose values moved."""
+        cache = getattr(self, "_pull_cache", None)
+        if not self.is_sparse or cache is None:
+            # first pull (every row is stale) or a dense table: everything
+            self._pull_cache = self.get(option=option)
+            return np.arange(self.num_row, dtype=np.int64), self._pull_cache.copy()
+        prev = cache.copy()
+        self.get(out=cache, option=option)          # the servers overwrite only the stale rows
+        changed = np.flatnonzero((cache != prev).any(axis=1)).astype(np.int64)
+        return changed, cache[changed]
 
 
 class HostKVTable(_HostTable):

@@ -111,3 +111,29 @@ def test_set_flag_and_identity(mv_host):
     mv.aggregate(x)                                   # world size 1: identity
     assert np.array_equal(x, np.arange(6, dtype=np.float32))
     mv.dashboard_display()                            # native Dashboard::Display must not raise
+
+
+def test_host_backend_has_the_async_spellings(mv_host):
+    """Scripts written against the device backend (handles + wait) run unchanged on the host backend."""
+    mv = mv_host
+    a = mv.ArrayTable(8, "float32")
+    a.wait(a.add_async(np.ones(8, np.float32)))
+    mv.barrier()
+    h, out = a.get_async()
+    a.wait(h)
+    assert np.array_equal(out, np.ones(8, np.float32))
+    m = mv.MatrixTable(6, 3, "float32", is_sparse=True)
+    m.wait(m.add_rows_async([2, 5], np.full((2, 3), 2.0, np.float32)))
+    mv.barrier()
+    h, rows = m.get_rows_async([5, 2, 0])
+    m.wait(h)
+    assert np.array_equal(rows, np.array([[2, 2, 2], [2, 2, 2], [0, 0, 0]], np.float32))
+    ids, vals = m.get_stale()                      # first pull: everything
+    assert ids.size == 6
+    m.add_rows([1], np.ones((1, 3), np.float32))
+    mv.barrier()
+    ids, vals = m.get_stale()
+    assert ids.tolist() == [1] and np.array_equal(vals, np.ones((1, 3), np.float32))
+    ids, vals = m.get_stale()
+    assert ids.size == 0 and vals.shape == (0, 3)
+    m.finish_train()
