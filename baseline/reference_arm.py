@@ -10,13 +10,8 @@ build exists at baseline/_ref/bin/wordembedding this arm runs it.
 """
 from __future__ import annotations
 
-import json
 import os
-import re
 import subprocess
-import sys
-import tempfile
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BIN = os.path.join(ROOT, "baseline", "_ref", "bin", "wordembedding")

@@ -171,7 +171,6 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    import numpy as np
     import torch
     import multiverso_b200 as mv
     from multiverso_b200.models.wordembedding import (WordEmbedding, WordEmbeddingOption,

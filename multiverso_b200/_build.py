@@ -12,10 +12,8 @@ Objects are cached under ``build/`` and rebuilt only when a source or header is 
 """
 from __future__ import annotations
 
-import os
 import shutil
 import subprocess
-import sys
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 
