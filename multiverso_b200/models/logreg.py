@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
 
@@ -89,6 +89,47 @@ class LogRegConfig:
             setattr(self, key, float(value))
         else:
             setattr(self, key, value)
+
+
+# Dense problems whose forward / backward are real GEMMs (many classes or wide inputs) go through
+# the library GEMM -- cuBLAS on the tensor cores -- instead of the CUDA-core K8 kernel, which is
+# written for the reference's shapes (MNIST: 785 x 10) and holds at most 64 classes per sample.
+GEMM_PATH_MIN_CLASSES = 65
+GEMM_PATH_MIN_WORK = 1 << 26          # n * dim * out multiply-adds per minibatch
+
+
+def dense_gemm_step(x: torch.Tensor, labels: torch.Tensor, w: torch.Tensor, grad: Optional[torch.Tensor],
+                    objective: int, out: int):
+    """One dense minibatch as two GEMMs: logits = X W^T, then (if ``grad`` is given)
+    grad += (P - Y)^T X / n.  Same maths as K8 / Objective::Predict + Gradient
+    (objective.cpp:64-233): objective 0 linear (squared loss), 1 sigmoid, 2 softmax.
+    Returns (loss_sum, n_correct, predictions[n x out]).  Pure torch: runs on any device."""
+    n, dim = x.shape
+    W = w.view(out, dim)
+    logits = x @ W.t()
+    if out == 1:
+        target = labels.view(n, 1).to(logits.dtype)
+    else:
+        target = torch.zeros_like(logits)
+        target.scatter_(1, labels.view(n, 1).to(torch.int64), 1.0)
+    if objective == 2 and out > 1:
+        p = torch.softmax(logits, dim=1)
+        loss = -torch.log(p.gather(1, labels.view(n, 1).to(torch.int64)).clamp_min(1e-30)).sum()
+    elif objective >= 1:
+        p = torch.sigmoid(logits)
+        loss = -(target * torch.log(p.clamp_min(1e-30)) + (1 - target) * torch.log((1 - p).clamp_min(1e-30))).sum()
+    else:
+        p = logits
+        loss = 0.5 * ((p - target) ** 2).sum()
+    if out > 1:
+        correct = (p.argmax(dim=1) == labels.to(torch.int64)).sum()
+    elif objective >= 1:
+        correct = ((p.view(-1) > 0.5) == (labels > 0.5)).sum()
+    else:
+        correct = ((p.view(-1) - labels).abs() < 0.5).sum()
+    if grad is not None:
+        grad.view(out, dim).addmm_((p - target).t(), x, alpha=1.0 / n)
+    return loss, correct, p
 
 
 class LogRegModel:
@@ -182,6 +223,15 @@ class LogRegModel:
 
     def forward_backward_dense(self, x, labels, train=True, pred=None):
         n = labels.numel()
+        if self.out >= GEMM_PATH_MIN_CLASSES or n * self.dim * self.out >= GEMM_PATH_MIN_WORK:
+            loss, correct, p = dense_gemm_step(x.view(n, self.dim), labels, self._weights(),
+                                               self.grad if train else None, self.objective, self.out)
+            self.loss += loss
+            self.correct += correct.to(torch.int32)
+            if pred is not None:
+                pred.view(n, self.out).copy_(p)
+            self.kernel_launches += 2 if train else 1      # library GEMMs, counted like launches
+            return
         self._ensure_err(n)
         a = N.LrDense()
         a.x, a.labels, a.n, a.dim, a.out = x.data_ptr(), labels.data_ptr(), n, self.dim, self.out
