@@ -19,11 +19,23 @@ from .. import _native as N
 
 
 def get_gemm_supported() -> bool:
+    """True when the fused tcgen05 kernel can run here (sm_100a device present)."""
+    if not torch.cuda.is_available():
+        return False
     return bool(N.cuda_lib().mvb_get_gemm_supported())
 
 
 def get_gemm(table, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-    """``x``: [M, K] fp32 CUDA, ``table``: MatrixDeviceTable with num_col == K. Returns [M, num_row]."""
+    """``x``: [M, K] fp32 CUDA, ``table``: MatrixDeviceTable with num_col == K. Returns [M, num_row].
+    On the host backend (no GPU) the same call is a plain Get followed by a matmul."""
+    from ..runtime import Runtime
+    if Runtime.get().backend == "host":
+        w = torch.as_tensor(table.get()).view(table.num_row, table.num_col).to(torch.float32)
+        y = torch.as_tensor(x, dtype=torch.float32) @ w.t()
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
     assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
     M, K = x.shape
     assert K == table.num_col and table.dtype == torch.float32

@@ -184,3 +184,46 @@ def test_logreg_dense_gemm_step_matches_reference_maths(objective, out):
     assert int(correct) == exp_correct
     assert np.allclose(grad.view(out, dim).numpy(), exp_grad, atol=1e-5)
     assert p.shape == (n, out)
+
+
+def test_get_gemm_on_the_host_backend(mv_host):
+    import torch
+    mv = mv_host
+    t = mv.MatrixTable(12, 8, "float32")
+    w = np.arange(96, dtype=np.float32).reshape(12, 8) / 10
+    t.add(w)
+    mv.barrier()
+    x = torch.arange(24, dtype=torch.float32).view(3, 8)
+    y = mv.ops.get_gemm(t, x)
+    assert torch.allclose(y, x @ torch.from_numpy(w).t())
+    assert not mv.ops.get_gemm_supported()
+
+
+def test_ps_linear_autograd_and_push(mv_host):
+    """PSLinear: forward = x @ W^T against the table, backward returns dL/dx and pushes dL/dW * scale
+    into the table (default updater adds, so -lr performs the SGD step on the servers)."""
+    import torch
+    mv = mv_host
+    out_f, in_f, lr = 6, 4, 0.5
+    t = mv.MatrixTable(out_f, in_f, "float32")
+    w0 = torch.linspace(-1, 1, out_f * in_f).view(out_f, in_f)
+    t.add(w0.numpy())
+    mv.barrier()
+    layer = mv.ops.PSLinear(t, push_scale=-lr)
+    x = torch.randn(5, in_f, requires_grad=True)
+    target = torch.randn(5, out_f)
+    loss = ((layer(x) - target) ** 2).sum()
+    loss.backward()
+    # the same computation with a local weight
+    w_ref = w0.clone().requires_grad_(True)
+    x_ref = x.detach().clone().requires_grad_(True)
+    ((x_ref @ w_ref.t() - target) ** 2).sum().backward()
+    assert torch.allclose(x.grad, x_ref.grad, atol=1e-5)
+    mv.barrier()
+    w_new = torch.as_tensor(t.get()).view(out_f, in_f)
+    assert torch.allclose(w_new, w0 - lr * w_ref.grad, atol=1e-5)
+    # batched leading dimensions, no push
+    frozen = mv.ops.PSLinear(t, push_scale=None)
+    y = frozen(torch.ones(2, 3, in_f))
+    assert y.shape == (2, 3, out_f) and torch.allclose(y[0, 0], w_new.sum(dim=1), atol=1e-5)
+    assert "out_features=6" in repr(frozen)
