@@ -30,11 +30,16 @@
 #include "multiverso/apps/app_api.h"
 #include "multiverso/device/device.h"
 #include "multiverso/multiverso.h"
+#include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
 #include "multiverso/util/timer.h"
 #include "option.h"
 #include "trainer.h"
 
+namespace multiverso {
+MV_DECLARE_bool(sync);
+inline bool SyncMode() { return MV_CONFIG(sync); }   // -sync=true: BSP server
+}  // namespace multiverso
 using multiverso::Log;
 using namespace wordembedding;
 namespace dev = multiverso::device;
@@ -55,7 +60,14 @@ constexpr int64_t kWordCountKey = 4;
 template <typename T>
 class DeviceBuffer {
  public:
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
   ~DeviceBuffer() { dev::DeviceFree(ptr_); }
+  void Swap(DeviceBuffer& other) {
+    std::swap(ptr_, other.ptr_);
+    std::swap(cap_, other.cap_);
+  }
   T* Reserve(size_t n) {
     if (n > cap_) {
       dev::DeviceFree(ptr_);
@@ -112,11 +124,13 @@ class BlockQueue {   // bounded hand-off loader -> training loop (block_queue.cp
   std::condition_variable not_full_, not_empty_;
 };
 
-void LoaderMain(void* dict, const Option& opt, int rank, int size, int64_t block_tokens, BlockQueue* q) {
+void LoaderMain(void* dict, const Option& opt, int rank, int size, bool full_rounds_only, int64_t block_tokens,
+                BlockQueue* q) {
   const std::string sw = (opt.stopwords && !opt.sw_file.empty()) ? opt.sw_file : "";
   void* corpus = MVA_CorpusOpen(dict, opt.train_file.c_str(), sw.c_str(), opt.sample, 12345 + rank);
   if (corpus == nullptr) Log::Fatal("cannot open the corpus %s\n", opt.train_file.c_str());
   int64_t i = 0;
+  std::unique_ptr<DataBlock> held;
   for (int epoch = 0; epoch < opt.epoch; ++epoch) {
     if (epoch > 0) MVA_CorpusReset(corpus);
     for (;; ++i) {
@@ -125,13 +139,20 @@ void LoaderMain(void* dict, const Option& opt, int rank, int size, int64_t block
       int64_t words = 0;
       const int64_t n = MVA_CorpusNextBlock(corpus, b->tokens.data(), block_tokens, &words);
       if (n <= 0) break;
-      if (i % size != rank) continue;
-      b->tokens.resize(n);
-      b->corpus_words = words;
-      b->epoch = epoch;
-      q->Push(std::move(b));
+      if (i % size == rank) {
+        b->tokens.resize(n);
+        b->corpus_words = words;
+        b->epoch = epoch;
+        held = std::move(b);
+      }
+      // BSP mode: every worker must issue the same number of table operations, so a block is only
+      // released once its whole round (one block per rank) exists; an incomplete last round is dropped
+      if (!full_rounds_only || (i + 1) % size == 0) {
+        if (held) q->Push(std::move(held));
+      }
     }
   }
+  if (held && !full_rounds_only) q->Push(std::move(held));
   MVA_CorpusClose(corpus);
   q->Close();
 }
@@ -321,7 +342,7 @@ int main(int argc, char* argv[]) {
     if (size > 1 && !delta_fused) Log::Fatal("block mode on several GPUs needs -size to be a multiple of 4\n");
     const int64_t block_tokens = std::max<int64_t>(1024, opt.data_block_size / kBytesPerToken);
     BlockQueue queue(opt.max_preload_data_size);
-    std::thread loader(LoaderMain, dict, std::cref(opt), rank, size, block_tokens, &queue);
+    std::thread loader(LoaderMain, dict, std::cref(opt), rank, size, multiverso::SyncMode() && size > 1, block_tokens, &queue);
 
     uint64_t block_seq = 0;
     auto next_prepared = [&]() -> std::unique_ptr<DataBlock> {   // Pop + PrepareData on a host thread

@@ -22,9 +22,14 @@
 #include "model.h"
 #include "multiverso/apps/app_api.h"
 #include "multiverso/multiverso.h"
+#include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
 #include "multiverso/util/timer.h"
 
+namespace multiverso {
+MV_DECLARE_bool(sync);
+inline bool SyncMode() { return MV_CONFIG(sync); }   // -sync=true: BSP server
+}  // namespace multiverso
 using multiverso::Log;
 using namespace logreg;
 
@@ -82,12 +87,26 @@ bool ReadWindow(SampleReader* reader, const Configure& cfg, bool need_keys, Wind
   return !w->empty();
 }
 
-// Next window that belongs to this rank (windows are dealt round-robin).
-bool ReadMyWindow(SampleReader* reader, const Configure& cfg, bool need_keys, int rank, int size, int64_t* index,
-                  Window* w) {
-  while (ReadWindow(reader, cfg, need_keys, w))
-    if ((*index)++ % size == rank) return true;
-  return false;
+// Next window that belongs to this rank (windows are dealt round-robin). In BSP mode every worker
+// must issue the same number of table operations, so this rank's window of a round is only released
+// once the whole round (one window per rank) has been read; an incomplete last round is dropped.
+bool ReadMyWindow(SampleReader* reader, const Configure& cfg, bool need_keys, int rank, int size, bool full_rounds_only,
+                  int64_t* index, Window* w) {
+  Window scratch, mine;
+  bool have_mine = false;
+  while (ReadWindow(reader, cfg, need_keys, &scratch)) {
+    const int64_t i = (*index)++;
+    if (i % size == rank) {
+      std::swap(mine, scratch);
+      have_mine = true;
+      if (!full_rounds_only) break;
+    }
+    if (full_rounds_only && (i + 1) % size == 0 && have_mine) break;
+    if (full_rounds_only && (i + 1) % size == 0) have_mine = false;
+  }
+  if (have_mine && full_rounds_only && *index % size != 0) have_mine = false;   // the round never completed
+  if (have_mine) std::swap(*w, mine);
+  return have_mine;
 }
 
 double Test(const Configure& cfg, Model* model, int rank, int size) {
@@ -137,6 +156,11 @@ int main(int argc, char* argv[]) {
   std::unique_ptr<Model> model = Model::Create(cfg);
   if (!cfg.init_model_file.empty()) model->Load(cfg.init_model_file);
   const bool need_keys = cfg.use_ps && (cfg.sparse || cfg.ftrl());
+  const bool full_rounds_only = cfg.use_ps && size > 1 && multiverso::SyncMode();
+  if (need_keys && size > 1 && multiverso::SyncMode())
+    Log::Fatal("logreg: the BSP server (-sync=true) needs every worker to address every server in every step; the sparse "
+               "parameter-server tables only address the owners of the keys a minibatch touches. Run sparse / FTRL "
+               "models in async mode (the reference's mode for them), or dense ones in BSP.\n");
   if (rank == 0)
     Log::Info("logreg: %lld inputs (+bias), %d outputs, objective %s, regular %s, updater %s, %s input, %s, "
               "minibatch %d, %d epoch(s)\n",
@@ -156,9 +180,9 @@ int main(int argc, char* argv[]) {
     int64_t seen = 0, shown = 0, correct = 0, window_index = 0;
     double loss = 0;
     Window cur, next;
-    bool have = ReadMyWindow(&reader, cfg, need_keys, rank, size, &window_index, &cur);
+    bool have = ReadMyWindow(&reader, cfg, need_keys, rank, size, full_rounds_only, &window_index, &cur);
     while (have) {
-      const bool have_next = ReadMyWindow(&reader, cfg, need_keys, rank, size, &window_index, &next);
+      const bool have_next = ReadMyWindow(&reader, cfg, need_keys, rank, size, full_rounds_only, &window_index, &next);
       model->BeginWindow(cur.keys, have_next ? &next.keys : nullptr);
       for (const MiniBatch& b : cur.batches) {
         const BatchResult r = model->Update(b);

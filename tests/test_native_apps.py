@@ -290,3 +290,33 @@ def test_logreg_usage_and_bad_config(tmp_path):
     bad.write_text("output_size=2\n")
     r = subprocess.run([os.path.join(BIN, "logreg"), str(bad)], capture_output=True, text=True, timeout=30)
     assert r.returncode == 2 and "input_size" in r.stderr
+
+
+# ------------------------------------------------------------------------------------ BSP mode
+def test_logreg_dense_ps_bsp_equal_step_counts(lr_data):
+    """-sync=true: every worker must issue the same number of Adds / Gets. 3000 samples / 10 per
+    minibatch / 2 per window = 150 windows do not divide by 4 ranks: the incomplete last round is
+    dropped, every rank trains on the same number of samples and nothing deadlocks."""
+    d = lr_data
+    res = run(4, os.path.join(BIN, "logreg"),
+              dense_cfg(d, "dense_bsp", use_ps="true", pipeline="false", sync_frequency=2), "-sync=true")
+    assert len({r["samples"] for r in res}) == 1 and res[0]["samples"] == 3 * (150 // 4) * 20
+    for r in res:
+        assert r["test_error"] < 0.12, r
+
+
+def test_logreg_sparse_ps_rejects_bsp(lr_data):
+    d = lr_data
+    cfg = sparse_cfg(d, "sp_bsp", use_ps="true")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", "2", "--timeout", "60", "--",
+                        os.path.join(BIN, "logreg"), cfg, "-sync=true"], capture_output=True, text=True, timeout=90)
+    assert r.returncode != 0 and "async mode" in (r.stdout + r.stderr)
+
+
+def test_wordembedding_bsp_complete_rounds(corpus):
+    d, path = corpus
+    res = run(3, os.path.join(BIN, "wordembedding"), "-train_file", path, "-size", "16", "-epoch", "2", "-threads", "2",
+              "-min_count", "1", "-data_block_size", "30000", "-cbow", "0", "-is_pipeline", "0", "-sync=true")
+    assert len({r["blocks"] for r in res}) == 1 and res[0]["blocks"] > 0      # same number of blocks on every rank
+    for r in res:
+        assert r["epoch_loss"][-1] < r["epoch_loss"][0]
