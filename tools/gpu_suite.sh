@@ -103,6 +103,35 @@ with open("gpurun_out/topics.txt", "w") as f:
         t = rng.integers(20); ws = rng.integers(50, size=rng.integers(5, 20))
         f.write(" ".join(f"t{t}w{w}" for w in ws) + "\n")
 PY
+  python - <<'PY'
+import numpy as np
+rng = np.random.default_rng(1)
+D, C, N = 20, 4, 6000
+Wt = rng.normal(size=(C, D)); X = rng.normal(size=(N, D)); y = (X @ Wt.T).argmax(1)
+for name, lo, hi in (("train", 0, 5000), ("test", 5000, 6000)):
+    with open(f"gpurun_out/lr_{name}.txt", "w") as f:
+        for xi, yi in zip(X[lo:hi], y[lo:hi]):
+            f.write(str(int(yi)) + " " + " ".join("%.4f" % v for v in xi) + "\n")
+for ps in ("false", "true"):
+    open(f"gpurun_out/lr_ps_{ps}.config", "w").write(f"""input_size=20
+output_size=4
+objective_type=softmax
+regular_type=L2
+updater_type=sgd
+learning_rate=0.5
+train_epoch=3
+minibatch_size=20
+use_ps={ps}
+pipeline=true
+sync_frequency=2
+train_file=gpurun_out/lr_train.txt
+test_file=gpurun_out/lr_test.txt
+output_file=gpurun_out/lr_{ps}.out
+output_model_file=gpurun_out/lr_{ps}.model
+""")
+PY
+  timeout 200 build/bin/logreg_gpu gpurun_out/lr_ps_false.config > gpurun_out/lr_gpu_local.log 2>&1; echo "logreg_gpu local rc=$?"; grep '^{' gpurun_out/lr_gpu_local.log | cut -c1-300
+  timeout 200 $L build/bin/logreg_gpu gpurun_out/lr_ps_true.config > gpurun_out/lr_gpu_ps_n$NG.log 2>&1; echo "logreg_gpu ps rc=$?"; grep '^{' gpurun_out/lr_gpu_ps_n$NG.log | head -8 | cut -c1-300
   timeout 300 $L build/bin/wordembedding_gpu -train_file gpurun_out/topics.txt -output gpurun_out/topics_vec.txt -size 32 -cbow 0 -negative 5 -epoch 3 -min_count 1 -data_block_size 300000 > gpurun_out/we_gpu_n$NG.log 2>&1; echo "wordembedding_gpu rc=$?"; grep '^{' gpurun_out/we_gpu_n$NG.log | head -8 | cut -c1-400
   ;;
 probe)
