@@ -2,10 +2,13 @@
 #include "multiverso/table_interface.h"
 #include "multiverso/actor.h"
 #include "multiverso/dashboard.h"
+#include "multiverso/util/configure.h"
 #include "multiverso/util/log.h"
 #include "multiverso/zoo.h"
 
 namespace multiverso {
+
+MV_DEFINE_double(request_stall_warn_s, 60.0, "log a line whenever a table request has waited this long for its servers");
 
 WorkerTable::WorkerTable() { table_id_ = Zoo::Get()->RegisterTable(this); }
 WorkerTable::~WorkerTable() = default;
@@ -75,7 +78,14 @@ void WorkerTable::Wait(int id) {
     if (it == waiting_.end()) return;   // already waited
     w = it->second.get();
   }
-  w->Wait();
+  // A request that waits this long is worth a line in the log (the reference hangs silently when a
+  // server died or a BSP schedule is uneven); the wait itself has no deadline.
+  double waited = 0;
+  while (!w->WaitFor(MV_CONFIG(request_stall_warn_s))) {
+    waited += MV_CONFIG(request_stall_warn_s);
+    Log::Error("table %d: request %d still waits for %d server repl%s after %.0f s\n", table_id_, id, w->outstanding(),
+               w->outstanding() == 1 ? "y" : "ies", waited);
+  }
   OnRequestDone(id);
   std::lock_guard<std::mutex> lk(mu_);
   waiting_.erase(id);

@@ -25,6 +25,7 @@ _DEFAULTS: Dict[str, Any] = {
     "machine_file": "", "port": 55555,
     # --- B200 additions -------------------------------------------------------------------
     "barrier_timeout_s": 120.0,   # watchdog on device-side spins
+    "request_stall_warn_s": 60.0,  # host backend: log a line whenever a table request has waited this long
     "kv_capacity": 1 << 20,       # slots per KV shard
     "async_one_sided": True,      # async mode: stateless updaters push with red.add
     "nvls": True,                 # use NVSwitch multicast (multimem.*) for MV_Aggregate when available

@@ -132,3 +132,13 @@ def test_cpp_examples_compile_and_run(tmp_path):
         subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
                         os.path.join(ROOT, "examples", "cpp", "device_tables.cpp"), "-o", str(tmp_path / "device_tables"),
                         f"-L{lib}", "-lmvdevice", "-lmultiverso", "-lmvb200", f"-Wl,-rpath,{lib}"], check=True)
+
+
+def test_stalled_request_is_reported():
+    """A BSP schedule with unequal step counts (rank 1 issues one Add more than rank 0 before rank 0
+    reaches shutdown) makes a request wait; the waiting rank must say which table / request / how many
+    servers it is waiting for (-request_stall_warn_s) instead of hanging silently, and the run still
+    completes once the other rank's FinishTrain arrives."""
+    script = os.path.join(ROOT, "tests", "mp_host_stall.py")
+    out = run_mp(2, sys.executable, script)
+    assert "still waits for" in out and out.count("stall ok") == 2
