@@ -7,9 +7,16 @@ namespace multiverso {
 Monitor::Monitor(const std::string& name) : name_(name) { Dashboard::AddMonitor(name, this); }
 
 std::string Monitor::info_string() const {
+  long long count;
+  double elapse;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    count = count_;
+    elapse = elapse_;
+  }
   std::ostringstream ss;
-  ss << "[Monitor] " << name_ << ": count = " << count_ << " elapse = " << elapse_
-     << "ms average = " << average() << "ms";
+  ss << "[Monitor] " << name_ << ": count = " << count << " elapse = " << elapse
+     << "ms average = " << (count ? elapse / count : 0.0) << "ms";
   return ss.str();
 }
 

@@ -20,16 +20,26 @@ class Monitor {
     elapse_ += ms;
     ++count_;
   }
-  double average() const { return count_ ? elapse_ / count_ : 0.0; }
+  // Readers take the same lock as Add(): monitors are read (Display) while actors still update them.
+  double average() const {
+    std::lock_guard<std::mutex> lk(mu_);
+    return count_ ? elapse_ / count_ : 0.0;
+  }
   const std::string& name() const { return name_; }
-  double elapse() const { return elapse_; }
-  long long count() const { return count_; }
+  double elapse() const {
+    std::lock_guard<std::mutex> lk(mu_);
+    return elapse_;
+  }
+  long long count() const {
+    std::lock_guard<std::mutex> lk(mu_);
+    return count_;
+  }
   std::string info_string() const;
 
  private:
   std::string name_;
   Timer timer_;
-  std::mutex mu_;
+  mutable std::mutex mu_;
   double elapse_ = 0.0;
   long long count_ = 0;
 };
