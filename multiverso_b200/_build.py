@@ -164,6 +164,15 @@ def build_device_rt(verbose: bool = False) -> Path:
             print("[build] g++ device_rt -> libmvdevice.so", flush=True)
         _run([cxx, *CXX_FLAGS, *inc, "-shared", *map(str, srcs), "-o", str(out), f"-L{LIBDIR}", "-lmultiverso",
               "-lmvb200", "-Wl,-rpath,$ORIGIN"], "link libmvdevice.so")
+    # the reference's C API served by the device plane (what a Lua / C# / ctypes binding can load
+    # instead of libmultiverso.so to get HBM-resident tables)
+    capi = sorted((srcdir / "c_api_gpu").glob("*.cpp"))
+    capi_out = LIBDIR / "libmultiverso_gpu.so"
+    if capi and _newer(capi + hdrs + [out], capi_out):
+        if verbose:
+            print("[build] g++ c_api_gpu -> libmultiverso_gpu.so", flush=True)
+        _run([cxx, *CXX_FLAGS, *inc, "-shared", *map(str, capi), "-o", str(capi_out), f"-L{LIBDIR}", "-lmvdevice",
+              "-lmultiverso", "-lmvb200", "-Wl,-rpath,$ORIGIN"], "link libmultiverso_gpu.so")
     bindir = BUILD / "bin"
     bindir.mkdir(parents=True, exist_ok=True)
     # executables: csrc/device_rt/{tools,apps}/<name>/*.cpp -> build/bin/<name>; an optional SOURCES

@@ -68,3 +68,17 @@ def test_c_api_roundtrip_through_ctypes():
     lib.MV_GetMatrixTableAll(m, full.ctypes.data_as(ctypes.c_void_p), 12)
     assert full.reshape(4, 3)[[1, 3]].sum() == 6 and full.sum() == 6
     lib.MV_ShutDownEx(0)
+
+
+def test_gpu_c_api_library_exports_the_reference_abi():
+    """libmultiverso_gpu.so (the reference's C API served by the device plane) must export exactly the
+    entry points the bindings bind to, unmangled, so that it can be loaded in place of libmultiverso.so."""
+    import subprocess
+    from multiverso_b200 import _build
+    _build.build_device_rt()
+    lib = os.path.join(ROOT, "multiverso_b200", "_lib", "libmultiverso_gpu.so")
+    assert os.path.exists(lib)
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert set(REFERENCE_C_API) <= exported, set(REFERENCE_C_API) - exported
+    assert not [n for n in exported if n.startswith("MV_") and n not in REFERENCE_C_API]

@@ -94,6 +94,7 @@ devrt)
   for sync in true false; do
     timeout 260 $L build/bin/mv_device_test all -sync=$sync > gpurun_out/devrt_n${NG}_sync_$sync.log 2>&1; echo "mv_device_test sync=$sync rc=$?"; grep -E "PASS|FAIL|EXPECT" gpurun_out/devrt_n${NG}_sync_$sync.log | head -12
   done
+  timeout 200 $L python tools/check_gpu_c_api.py > gpurun_out/gpu_c_api_n$NG.log 2>&1; echo "gpu c api rc=$?"; grep -E "gpu c api ok|Error|FATAL" gpurun_out/gpu_c_api_n$NG.log | head -8
   timeout 200 $L build/bin/mv_device_test bench -sync=true > gpurun_out/devrt_bench_n$NG.log 2>&1; echo "mv_device_test bench rc=$?"; grep '^{' gpurun_out/devrt_bench_n$NG.log | head -8
   python - <<'PY'
 import numpy as np
