@@ -26,6 +26,24 @@ kv = mv.KVTable("int64", "float32")
 kv.add([1, 2, 1000003], [1.0, 2.0, 0.5])
 mv.barrier()
 assert np.allclose(kv.get([1, 2, 1000003, 9]), [W, 2 * W, 0.5 * W, 0])
+# checkpoint: every server writes its shard; a later load restores the table on every rank
+import tempfile
+ckpt = os.path.join(tempfile.gettempdir(), f"mv_mp_ckpt_{os.environ.get('MV_PORT', '0')}")
+before = t.get().copy()
+assert mv.save_table(t, ckpt)
+t.add(d)
+mv.barrier()
+assert not np.array_equal(t.get(), before)
+assert mv.load_table(t, ckpt)
+assert np.array_equal(t.get(), before)
+mv.barrier()
+if mv.rank() == 0:
+    for s in range(mv.num_servers()):
+        os.remove(f"{ckpt}.shard{s}")
+# the device backend's async spellings on the host backend
+h, rows = m.get_rows_async([0, 10])
+m.wait(h)
+assert np.array_equal(rows, exp[[0, 10]])
 x = np.full(10, float(mv.rank() + 1), np.float64)
 mv.aggregate(x)
 assert np.allclose(x, W * (W + 1) / 2)
