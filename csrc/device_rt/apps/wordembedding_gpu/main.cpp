@@ -429,7 +429,9 @@ int main(int argc, char* argv[]) {
     dev::Barrier();
     seconds = wall.elapse() * 1e-3;
     if (rank == 0 && !opt.output_file.empty()) SaveEmbedding(opt, dict, vocab.size, model.input.get());
-    dev::Barrier();
+    // writing a large vocabulary as text can take minutes: the others wait on the control plane (no
+    // deadline) rather than in a device barrier (watchdog)
+    multiverso::MV_Barrier();
     launches = model.launches;
   }   // tables are destroyed (collectively) before ShutDown
   std::string losses;
