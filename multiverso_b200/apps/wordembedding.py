@@ -192,6 +192,9 @@ def run(argv: List[str]) -> dict:
     elapsed = time.time() - t0
     if opt.output_file:
         we.save_embedding(opt.output_file, dictionary.words() if rank == 0 else None, binary=opt.output_binary)
+        # writing a large vocabulary as text takes minutes on rank 0: the other ranks wait on the control
+        # plane (no watchdog) so that shutdown's device barrier finds everybody already there
+        mv.runtime.Runtime.get().host_barrier()
     stats = {"words": words_done, "seconds": elapsed, "words_per_sec": words_done / max(elapsed, 1e-9),
              "vocab": dictionary.size, "rank": rank}
     if rank == 0:
