@@ -21,6 +21,7 @@ B200 mapping
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -100,14 +101,20 @@ class WordEmbedding:
         self.dev = rt.device
         self.W = max(rt.num_workers(), 1)
         D = self.D
+        # Row pitch of the tables. Experiment knob (off by default, to be measured): MVB_WE_ROW_PAD=32 pads
+        # every row to a multiple of 32 floats (300 -> 320: 1280-byte rows, so the TMA bulk loads / reductions
+        # of K7 are 128-byte aligned); the kernels take `dim` and `ld` separately, the padding is never read.
+        pad = int(os.environ.get("MVB_WE_ROW_PAD", "0"))
+        self.LD = (D + pad - 1) // pad * pad if pad > 1 else D
+        LD = self.LD
         # PrepareParameterTables (communicator.cpp:17-32)
-        self.input_table = MatrixDeviceTable(self.V, D, "float32", updater="default",
+        self.input_table = MatrixDeviceTable(self.V, LD, "float32", updater="default",
                                              min_value=-0.5 / D, max_value=0.5 / D, seed=seed)
-        self.output_table = MatrixDeviceTable(self.V, D, "float32", updater="default", init_value=0.0)
+        self.output_table = MatrixDeviceTable(self.V, LD, "float32", updater="default", init_value=0.0)
         self.g2_in = self.g2_out = None
         if option.use_adagrad:
-            self.g2_in = MatrixDeviceTable(self.V, D, "float32", updater="default", init_value=0.0)
-            self.g2_out = MatrixDeviceTable(self.V, D, "float32", updater="default", init_value=0.0)
+            self.g2_in = MatrixDeviceTable(self.V, LD, "float32", updater="default", init_value=0.0)
+            self.g2_out = MatrixDeviceTable(self.V, LD, "float32", updater="default", init_value=0.0)
         self.wordcount_table = KVDeviceTable("int64", "int64", capacity=1024)
         if word_counts is None:
             word_counts = 1.0 / np.arange(1, self.V + 1, dtype=np.float64)   # Zipf
@@ -194,7 +201,7 @@ class WordEmbedding:
             with monitor("WE_TRAIN_BLOCK", cuda=True):
                 self._launch(tokens, self.input_table.shard, self.output_table.shard,
                              None if self.g2_in is None else self.g2_in.shard,
-                             None if self.g2_out is None else self.g2_out.shard, self.D,
+                             None if self.g2_out is None else self.g2_out.shard, self.LD,
                              compute_loss=compute_loss)
             return
         if next_tokens is None and self._prefetched is None:
@@ -289,12 +296,12 @@ class WordEmbedding:
 
     def _train_prepared(self, tokens: torch.Tensor, st: dict, compute_loss: bool) -> None:
         with monitor("WE_TRAIN_BLOCK", cuda=True):
-            self._launch(tokens, st["cache_in"], st["cache_out"], st["g2i"], st["g2o"], self.D,
+            self._launch(tokens, st["cache_in"], st["cache_out"], st["g2i"], st["g2o"], self.LD,
                          st["map_in"], st["map_out"], st["neg_pool"], compute_loss)
 
     def _add_delta(self, st: dict) -> None:
         # AddDeltaParameter (communicator.cpp:206-249): delta = (trained - pulled) / W
-        o, D = self.opt, self.D
+        o, D = self.opt, self.LD
         inv = 1.0 / self.W
         in_ids, out_ids = st["in_ids"], st["out_ids"]
         if D % 4 == 0:
@@ -323,7 +330,7 @@ class WordEmbedding:
     def embeddings(self) -> torch.Tensor:
         """Whole input-embedding matrix [V, D] (SaveEmbedding pulls it in 100k-row batches)."""
         self.flush()
-        return self.input_table.get().view(self.V, self.D)
+        return self.input_table.get().view(self.V, self.LD)[:, :self.D]
 
     def save_embedding(self, path: str, words=None, binary: bool = False) -> None:
         """word2vec text / binary format (distributed_wordembedding.cpp:263-325); rank 0 only."""
@@ -335,7 +342,7 @@ class WordEmbedding:
             f.write(f"{self.V} {self.D}\n".encode())
             for lo in range(0, self.V, batch):
                 hi = min(self.V, lo + batch)
-                rows = self.input_table.get_rows(torch.arange(lo, hi, device=self.dev)).cpu().numpy()
+                rows = self.input_table.get_rows(torch.arange(lo, hi, device=self.dev))[:, :self.D].cpu().numpy()
                 for i in range(hi - lo):
                     w = words[lo + i] if words is not None else str(lo + i)
                     if binary:
