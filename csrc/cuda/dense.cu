@@ -372,6 +372,104 @@ __global__ void __launch_bounds__(256) get_dense_kernel(const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// K2, bulk-copy variant (EXPERIMENT, opt-in with MVB_GET_BULK=1; not measured yet).
+// The register kernel above keeps 4 x 16 B per thread in flight; a link-bound pull wants megabytes
+// in flight per GPU. Here ONE thread per CTA drives a ring of kBulkStages x kBulkChunk bytes of
+// shared memory with the bulk-copy engine: cp.async.bulk global(peer) -> smem (mbarrier
+// complete_tx), then cp.async.bulk smem -> global(local), no registers and no LSU instructions
+// on the data path; 1 CTA per SM (the ring takes the shared memory) x 148 SMs x 192 KB in flight.
+// ---------------------------------------------------------------------------
+constexpr int kBulkStages = 6;
+constexpr uint32_t kBulkChunk = 32 * 1024;
+
+MVB_DEVINL uint32_t dg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MVB_DEVINL void dg_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dg_smem_u32(bar)), "r"(count));
+}
+MVB_DEVINL void dg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+MVB_DEVINL void dg_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DG_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DG_DONE;\n"
+      "bra DG_WAIT_LOOP;\n"
+      "DG_DONE:\n"
+      "}\n" ::"r"(dg_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+MVB_DEVINL void dg_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dg_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(dg_smem_u32(bar))
+               : "memory");
+}
+MVB_DEVINL void dg_bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(dg_smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) get_dense_bulk_kernel(const __grid_constant__ DenseGetDev<T> g) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ uint64_t full[kBulkStages];
+  if (g.has_pads) {
+    if (threadIdx.x < g.S) {
+      const uint64_t* slot = reinterpret_cast<const uint64_t*>(g.pads.p[g.me]) +
+                             g.ch_done * MVB_MAX_RANKS + g.server_rank[threadIdx.x];
+      if (!spin_wait_ge(slot, g.epoch, g.budget)) { if (g.err) atomicExch(g.err, 4000 + threadIdx.x); };
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < kBulkStages; ++i) dg_mbar_init(&full[i], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const int groups = g.S;
+  const int grp = blockIdx.x % groups;
+  const int s = (g.me + 1 + grp) % groups;
+  const int64_t gidx = blockIdx.x / groups;
+  const int64_t gcount = (gridDim.x - grp + groups - 1) / groups;
+  const char* src = reinterpret_cast<const char*>(g.shard[s]);
+  char* dst = reinterpret_cast<char*>(g.out + g.off[s]);
+  const int64_t bytes = g.len[s] * (int64_t)sizeof(T);
+  const int64_t body = bytes / 16 * 16;                          // bulk copies move multiples of 16 bytes
+  const int64_t nchunks_total = (body + kBulkChunk - 1) / kBulkChunk;
+  // chunks gidx, gidx + gcount, ... of this server's segment belong to this CTA
+  const int64_t mine = nchunks_total > gidx ? (nchunks_total - gidx + gcount - 1) / gcount : 0;
+  auto chunk_off = [&](int64_t j) { return (gidx + j * gcount) * (int64_t)kBulkChunk; };
+  auto chunk_len = [&](int64_t j) {
+    const int64_t o = chunk_off(j);
+    return (uint32_t)((body - o) < (int64_t)kBulkChunk ? (body - o) : (int64_t)kBulkChunk);
+  };
+  auto load = [&](int64_t j) {
+    const int st = (int)(j % kBulkStages);
+    dg_mbar_expect_tx(&full[st], chunk_len(j));
+    dg_bulk_g2s(ring + (size_t)st * kBulkChunk, src + chunk_off(j), chunk_len(j), &full[st]);
+  };
+  for (int64_t j = 0; j < mine && j < kBulkStages; ++j) load(j);
+  for (int64_t j = 0; j < mine; ++j) {
+    const int st = (int)(j % kBulkStages);
+    dg_mbar_wait(&full[st], (uint32_t)((j / kBulkStages) & 1));
+    dg_bulk_s2g(dst + chunk_off(j), ring + (size_t)st * kBulkChunk, chunk_len(j));
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (j + kBulkStages < mine) {
+      // the stage is refilled only after the store has finished READING it; the other stages' loads
+      // are still in flight meanwhile
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      load(j + kBulkStages);
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores performed before the kernel ends
+  if (gidx == 0)                                                  // < 16 trailing bytes of the segment
+    for (int64_t b = body; b < bytes; ++b) dst[b] = src[b];
+}
+
 template <typename T>
 int launch_get(const MvbDenseGet* h, cudaStream_t st) {
   DenseGetDev<T> g{};
@@ -395,6 +493,26 @@ int launch_get(const MvbDenseGet* h, cudaStream_t st) {
   g.err = h->err_flag;
   double ts = h->timeout_s > 0 ? h->timeout_s : 60.0;
   g.budget = (long long)(ts * 1.9e9);
+  static const bool use_bulk = [] { const char* e = getenv("MVB_GET_BULK"); return e && atoi(e) != 0; }();
+  if (use_bulk) {
+    bool aligned = (reinterpret_cast<uintptr_t>(g.out) % 16) == 0;
+    for (int s = 0; s < h->nservers; ++s)
+      aligned = aligned && (reinterpret_cast<uintptr_t>(g.shard[s]) % 16 == 0) && ((g.off[s] * sizeof(T)) % 16 == 0);
+    if (aligned) {
+      const size_t smem = (size_t)kBulkStages * kBulkChunk;
+      static bool attr_set = false;
+      if (!attr_set) {
+        MVB_CUDA_CHECK(cudaFuncSetAttribute(get_dense_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      int64_t blocks = mvb_num_sms();
+      if (blocks < h->nservers) blocks = h->nservers;
+      blocks = (blocks + h->nservers - 1) / h->nservers * h->nservers;
+      get_dense_bulk_kernel<T><<<(int)blocks, 32, smem, st>>>(g);
+      MVB_CUDA_CHECK(cudaGetLastError());
+      return 0;
+    }
+  }
   const int threads = 256;
   int64_t blocks = (total / VecOf<T>::N / 4 + threads - 1) / threads;
   int64_t cap = (int64_t)mvb_num_sms() * 8;

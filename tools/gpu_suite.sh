@@ -88,6 +88,14 @@ tma_debug)
 ncu_tma)
   MVB_SGNS_VARIANT=10 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgns_tma -s 3 -c 1 -f -o gpurun_out/sgns_tma python bench.py --steps 2 --warmup 3 --no-table-bw > gpurun_out/ncu_sgns_tma.log 2>&1; echo "ncu_tma rc=$?"; tail -2 gpurun_out/ncu_sgns_tma.log
   ;;
+bulk)
+  # EXPERIMENT: dense Get through the bulk-copy engine (MVB_GET_BULK=1) -- correctness first, then time it
+  MVB_GET_BULK=1 timeout 600 python -m pytest tests/test_gpu_tables.py -q -m gpu -x -k "array or matrix" > gpurun_out/bulk_pytest.log 2>&1; echo "bulk pytest rc=$?"; tail -2 gpurun_out/bulk_pytest.log
+  if [ "$NG" -gt 1 ]; then L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+11))"; else L="python"; fi
+  for v in 0 1; do
+    MVB_GET_BULK=$v timeout 300 $L bench/matrix_bw.py > gpurun_out/matrix_bw_bulk$v.log 2>&1; echo "matrix_bw MVB_GET_BULK=$v rc=$?"; grep '^{' gpurun_out/matrix_bw_bulk$v.log | tail -1 | cut -c1-500
+  done
+  ;;
 devrt)
   # native C++ device runtime scenarios (BSP + async) and the native GPU wordembedding application
   if [ "$NG" -gt 1 ]; then L="python tools/mvrun.py -n $NG --timeout 200 --"; else L=""; fi
