@@ -261,10 +261,19 @@ typedef struct MvbSgns {
   uint64_t seed;
   float* loss_sum;           /* optional: += sum of -log sigma(..)         */
   unsigned long long* pair_count;  /* optional: += trained (input,target) samples */
-  int variant;               /* kernel variant: 0 auto, 1..5 = negatives held in registers, 10 = TMA pipeline */
+  int variant;               /* kernel variant: 0 auto, 1..5 = negatives held in registers, 10 = TMA pipeline
+                                (pair at a time), 20 = window-batched TMA pipeline (one centre per warp) */
+  int max_ctas;              /* 0 = one CTA per SM; > 0 caps the persistent grid (leaves SMs to the
+                                row pull / push kernels of the pipelined multi-GPU step)            */
+  /* optional per-WORD step scales in (0,1] (variant 20): caps the summed step of the Zipf-head rows
+     that collect more concurrent stale updates than plain SGD tolerates; NULL = 1 everywhere      */
+  const float* scale_in;
+  const float* scale_out;
 } MvbSgns;
 int mvb_sgns_train(const MvbSgns* a, void* stream);
 int mvb_sgns_train_tma(const MvbSgns* a, void* stream);   /* TMA bulk-copy pipeline variant */
+int mvb_sgns_train_win(const MvbSgns* a, void* stream);   /* window-batched TMA pipeline      */
+int mvb_sgns_win_inflight(int dim, int negative, int window, int max_ctas);  /* centre positions in flight */
 int mvb_build_alias_table(const double* weights_host, int n, float* prob_host, int* alias_host);
 
 /* ---- LogisticRegression (K8) ---------------------------------------------------- */

@@ -392,6 +392,7 @@ SgnsDev to_dev(const MvbSgns* h) {
 }  // namespace
 
 extern "C" int mvb_sgns_train_tma(const MvbSgns* h, void* stream);
+extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream);
 
 extern "C" int mvb_sgns_train(const MvbSgns* h, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -414,8 +415,13 @@ extern "C" int mvb_sgns_train(const MvbSgns* h, void* stream) {
     if (blocks > cap) blocks = cap;
     int variant = h->variant;
     if (const char* e = getenv("MVB_SGNS_VARIANT")) variant = atoi(e);
+    // window-batched pipeline (one centre position per warp, negatives shared by the position's contexts)
+    if ((variant == 20 || variant == 0) && h->negative <= 7 && h->window <= 15) {
+      int rc = mvb_sgns_train_win(h, stream);
+      if (rc != -22 && rc != -20 && rc != -21) return rc;   // else: rows do not fit the smem rings
+    }
     // measured on B200 (dim 300, K 5): TMA pipeline 52.3 vs best register variant 46.4 Mwords/s
-    if ((variant == 10 || variant == 0) && h->negative <= 6 && h->window <= 15) {
+    if ((variant == 10 || variant == 0 || variant == 20) && h->negative <= 6 && h->window <= 15) {
       int rc = mvb_sgns_train_tma(h, stream);
       if (rc != -22 && rc != -20 && rc != -21) return rc;   // else: rows do not fit the smem ring
     }

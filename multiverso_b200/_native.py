@@ -90,7 +90,8 @@ class Sgns(C.Structure):
         ("alias_prob", vp), ("alias_idx", vp), ("vocab", C.c_int), ("neg_pool", vp),
         ("neg_pool_size", C.c_int), ("hs_points", vp), ("hs_codes", vp), ("hs_len", vp),
         ("hs_max_code", C.c_int), ("map_in", vp), ("map_out", vp), ("seed", C.c_uint64),
-        ("loss_sum", vp), ("pair_count", vp), ("variant", C.c_int),
+        ("loss_sum", vp), ("pair_count", vp), ("variant", C.c_int), ("max_ctas", C.c_int),
+        ("scale_in", vp), ("scale_out", vp),
     ]
 
 

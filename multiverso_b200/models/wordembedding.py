@@ -145,7 +145,42 @@ class WordEmbedding:
         self._prefetched = None
         self._pending_side = False
         self.kernel_launches = 0
-        self.kernel_variant = 0     # 0 auto | 1,2,3,5 register kernel (negatives in flight) | 10 TMA pipeline
+        self.kernel_variant = 0     # 0 auto | 1,2,3,5 register kernel | 10 TMA pipeline (pair at a time) | 20 window-batched
+        self.max_ctas = 0           # > 0: cap K7's persistent grid (SMs left to the row pull / push kernels)
+        self.scale_in = self.scale_out = None
+        self._build_hot_row_cap()
+
+    # ------------------------------------------------------------------ hot-row step cap
+    def _build_hot_row_cap(self) -> None:
+        """Per-word step scales for the window-batched K7.
+
+        The kernel keeps P centre positions in flight per device (148 CTAs x 10 warps x 2 stages),
+        i.e. ~P (W+1) (context, centre) samples whose rows were read before any of their updates
+        landed.  The reference's Hogwild has <= `-threads` samples in flight; with ~18 000 the rows
+        of the Zipf head collect hundreds of same-direction stale steps per staleness window and
+        plain SGD overshoots (measured: loss diverges within 10 blocks on the raw Zipf corpus).
+        A row expected to collect G > cap concurrent updates gets its step scaled by cap / G, i.e.
+        its summed step per staleness window is what `cap` sequential samples would apply; every
+        other row (all but the few dozen hottest words) trains exactly as before.  cap = 0 disables."""
+        o = self.opt
+        cap = float(os.environ.get("MVB_WE_HOT_CAP", "128"))
+        if cap <= 0 or o.cbow or o.hs or o.use_adagrad or o.negative_num < 1:
+            return
+        pos = int(N.cuda_lib().mvb_sgns_win_inflight(C.c_int(self.D), C.c_int(o.negative_num),
+                                                     C.c_int(o.window_size), C.c_int(self.max_ctas)))
+        if pos <= 0:
+            return
+        f = self.counts / self.counts.sum()
+        q = np.power(self.counts, 0.75)
+        q /= q.sum()
+        pairs = pos * (o.window_size + 1.0)
+        g_in = pairs * f
+        g_out = pairs * (f + o.negative_num * q)
+        s_in = np.minimum(1.0, cap / np.maximum(g_in, 1e-30)).astype(np.float32)
+        s_out = np.minimum(1.0, cap / np.maximum(g_out, 1e-30)).astype(np.float32)
+        self.hot_rows_capped = (int((s_in < 1).sum()), int((s_out < 1).sum()))
+        self.scale_in = torch.from_numpy(s_in).to(self.dev)
+        self.scale_out = torch.from_numpy(s_out).to(self.dev)
 
     # ------------------------------------------------------------------ lr schedule
     def update_learning_rate(self) -> float:
@@ -182,6 +217,8 @@ class WordEmbedding:
         a.loss_sum = self.loss.data_ptr() if compute_loss else None
         a.pair_count = self.pairs.data_ptr()
         a.variant = self.kernel_variant
+        a.max_ctas = self.max_ctas
+        a.scale_in, a.scale_out = N.ptr(self.scale_in), N.ptr(self.scale_out)
         N.check(N.cuda_lib().mvb_sgns_train(C.byref(a), C.c_void_p(N.stream_ptr())), "mvb_sgns_train")
         self.kernel_launches += 1
 

@@ -77,6 +77,26 @@ perf)
   timeout 300 $L bench/matrix_perf.py > gpurun_out/matrix_perf.log 2>&1; echo "matrix_perf dense rc=$?"; grep '^{' gpurun_out/matrix_perf.log | tail -1 | cut -c1-500
   timeout 300 $L bench/matrix_perf.py --sparse > gpurun_out/matrix_perf_sparse.log 2>&1; echo "matrix_perf sparse rc=$?"; grep '^{' gpurun_out/matrix_perf_sparse.log | tail -1 | cut -c1-500
   ;;
+win)
+  # round 2: window-batched K7 (variant 20): numerics, 1-GPU bench vs the pair-at-a-time TMA kernel, ncu
+  timeout 600 python -m pytest tests/test_gpu_wordembedding.py -x -q > gpurun_out/pytest_we.log 2>&1; echo "pytest we rc=$?"; tail -8 gpurun_out/pytest_we.log
+  timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1_win.json 2> gpurun_out/bench_n1_win.err; echo "bench win rc=$?"; cut -c1-700 gpurun_out/bench_n1_win.json; tail -3 gpurun_out/bench_n1_win.err
+  MVB_SGNS_VARIANT=10 timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/bench_n1_tma.json 2> gpurun_out/bench_n1_tma.err; echo "bench tma rc=$?"; cut -c1-300 gpurun_out/bench_n1_tma.json
+  for nw in ${WIN_NW:-6 8}; do
+    MVB_WIN_NW=$nw timeout 300 python bench.py --steps 6 --warmup 3 --no-table-bw > gpurun_out/bench_n1_win_nw$nw.json 2> gpurun_out/bench_n1_win_nw$nw.err; echo "bench win nw=$nw rc=$?"; cut -c1-200 gpurun_out/bench_n1_win_nw$nw.json
+  done
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgns_win -s 3 -c 1 -f -o gpurun_out/sgns_win python bench.py --steps 2 --warmup 3 --no-table-bw > gpurun_out/ncu_sgns_win.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/ncu_sgns_win.log
+  ;;
+cap)
+  # hot-row step cap sweep: loss after the same number of blocks vs the pair-at-a-time kernel
+  timeout 600 python -m pytest tests/test_gpu_wordembedding.py -x -q > gpurun_out/pytest_we.log 2>&1; echo "pytest we rc=$?"; tail -5 gpurun_out/pytest_we.log
+  for st in ${CAP_STEPS:-6 22}; do
+  MVB_SGNS_VARIANT=10 timeout 300 python bench.py --steps $st --warmup 3 --no-table-bw > gpurun_out/cap_tma_s$st.json 2>/dev/null; python -c "import json;d=json.load(open('gpurun_out/cap_tma_s$st.json'));print('tma steps $st', round(d['value']/1e6,1), d['config']['loss_per_pair'])"
+  for c in ${CAPS:-32 64 128 256 512}; do
+    MVB_WE_HOT_CAP=$c timeout 300 python bench.py --steps $st --warmup 3 --no-table-bw > gpurun_out/cap_${c}_s$st.json 2>/dev/null; python -c "import json;d=json.load(open('gpurun_out/cap_${c}_s$st.json'));print('cap $c steps $st', round(d['value']/1e6,1), d['config']['loss_per_pair'])"
+  done
+  done
+  ;;
 refarm)
   timeout 1500 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_n1.json
   ;;
