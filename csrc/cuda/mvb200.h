@@ -269,11 +269,69 @@ typedef struct MvbSgns {
      that collect more concurrent stale updates than plain SGD tolerates; NULL = 1 everywhere      */
   const float* scale_in;
   const float* scale_out;
+  const int* neg_pool_size_ptr;  /* optional: pool size read on the DEVICE (mvb_we_prepare counts[2]);
+                                    variant 20 only, overrides neg_pool_size                          */
 } MvbSgns;
 int mvb_sgns_train(const MvbSgns* a, void* stream);
 int mvb_sgns_train_tma(const MvbSgns* a, void* stream);   /* TMA bulk-copy pipeline variant */
 int mvb_sgns_train_win(const MvbSgns* a, void* stream);   /* window-batched TMA pipeline      */
 int mvb_sgns_win_inflight(int dim, int negative, int window, int max_ctas);  /* centre positions in flight */
+/* ---- row mailboxes (rowbox.cu): device-side row Add with owner-side apply ------------- */
+typedef struct MvbRowBox {
+  MvbRowMap map;             /* the table's shards (fp32, num_col % 4 == 0, every rank worker + server)   */
+  int me;                    /* my rank == worker id == server id                                     */
+  int64_t cap;               /* rows per (owner, source) slot (>= rows of the largest shard)           */
+  int64_t slot_bytes;        /* mvb_rowbox_slot_bytes(cap, num_col)                                    */
+  void* box[MVB_MAX_RANKS];  /* rank r's mailbox slab: nservers x mvb_rowbox_slots() slots, peer mapped */
+  void* ack[MVB_MAX_RANKS];  /* rank r's ack array uint64[nservers], peer mapped                       */
+  int* seg;                  /* device scratch int[nservers + 1]                                       */
+  unsigned int* done;        /* device scratch uint[2], zero-initialised                               */
+  uint64_t* applied;         /* device uint64[nservers], zero-initialised: epochs applied per source   */
+  int* go;                   /* device scratch int[nservers]                                           */
+  int* err_flag;
+  double timeout_s;
+} MvbRowBox;
+int64_t mvb_rowbox_slot_bytes(int64_t cap, int64_t num_col);
+int mvb_rowbox_slots(void);            /* slots per (owner, source) pair (double-buffered: 2) */
+int mvb_rowbox_push_delta(const MvbRowBox* b, const int* ids, const int* n_ptr, int64_t n_max,
+                          const float* cur, const float* old, int64_t ld, float scale, uint64_t epoch,
+                          const MvbAddOpt* opt, int ctas_per_sm, void* stream);
+int mvb_rowbox_push_vals(const MvbRowBox* b, const int* ids, const int* n_ptr, int64_t n_max,
+                         const float* vals, int64_t ld, float scale, uint64_t epoch, const MvbAddOpt* opt,
+                         int ctas_per_sm, void* stream);
+int mvb_rowbox_poll(const MvbRowBox* b, int src, int wait, void* stream);
+int mvb_rowbox_apply(const MvbRowBox* b, int updater, float* shard, float* st0, float* st1,
+                     int64_t state_stride, int64_t row_lo, int src, int ctas_per_sm, void* stream);
+
+/* WordEmbedding block protocol on the device (we_block.cu): PrepareData without a host round trip,
+   row pull / delta push on the bulk-copy engine.  All counts live in device memory. */
+typedef struct MvbWePrep {
+  const int* tokens;         /* block of word ids, <0 = sentence break                          */
+  int64_t n_tokens;
+  int vocab;
+  int negative;              /* K: negative x |input| pool draws (0 = no pool)                 */
+  const float* alias_prob;   /* unigram^0.75 alias table                                      */
+  const int* alias_idx;
+  uint64_t seed;
+  uint32_t* bm_in;           /* scratch bitmaps [ceil(vocab/32)]                                */
+  uint32_t* bm_out;
+  int* chunk_sums;           /* scratch [ceil(vocab/32768)]                                     */
+  int* map_in;               /* out: word id -> slot in the input cache (-1 = absent) [vocab]   */
+  int* map_out;
+  int* ids_in;               /* out: slot -> word id [cap_in]                                   */
+  int* ids_out;              /*                      [cap_out]                                  */
+  int* neg_pool;             /* out: the block's negative pool [pool_cap]                       */
+  int64_t pool_cap;
+  int* counts;               /* out (device): [0] = n_in, [1] = n_out, [2] = n_pool             */
+  int64_t cap_in, cap_out;
+} MvbWePrep;
+int mvb_we_prepare(const MvbWePrep* p, void* stream);
+int mvb_we_prepare_launches(int negative);      /* kernels + memset/memcpy nodes it enqueues */
+int mvb_rows_pull_bulk(const MvbRowMap* m, int esz, const int* ids, const int* n_ptr, int64_t n_max,
+                       void* dst_a, void* dst_b, int64_t dst_ld, int max_ctas, void* stream);
+int mvb_rows_push_delta_bulk(const MvbRowMap* m, const int* ids, const int* n_ptr, int64_t n_max,
+                             const float* cur, const float* old, int64_t ld, float scale, int max_ctas,
+                             void* stream);
 int mvb_build_alias_table(const double* weights_host, int n, float* prob_host, int* alias_host);
 
 /* ---- LogisticRegression (K8) ---------------------------------------------------- */

@@ -54,6 +54,7 @@ struct WinDev {
   int vocab;
   const int* neg_pool;
   int neg_pool_size;
+  const int* neg_pool_size_ptr;
   const int* map_in;
   const int* map_out;
   const float* scale_in;    // optional per-word step scale (hot-row cap), indexed by word id
@@ -229,6 +230,7 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
     float** b_inptr = reinterpret_cast<float**>(smem + L.batch);
     int* b_rid = reinterpret_cast<int*>(smem + L.batch + 32 * 8);
     int* b_act = b_rid + 32 * kKO;
+    const int pool_n = a.neg_pool_size_ptr ? __ldg(a.neg_pool_size_ptr) : a.neg_pool_size;
     float* b_isc = reinterpret_cast<float*>(b_act + 32);
     float* b_osc = b_isc + 32;
     for (int64_t i0 = 0; i0 < nv; i0 += 32) {
@@ -265,7 +267,7 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
             if (k < a.ko) {
               const uint64_t r = hash64(prng ^ ((uint64_t)k * 0xD6E8FEB86659FD93ull));
               if (a.neg_pool) {
-                t[k] = __ldg(a.neg_pool + (r >> 8) % (uint64_t)a.neg_pool_size);
+                t[k] = pool_n > 0 ? __ldg(a.neg_pool + (r >> 8) % (uint64_t)pool_n) : -1;
               } else {
                 const uint32_t idx = (uint32_t)((r >> 32) % (uint64_t)a.vocab);
                 const float u = (float)(r & 0xFFFFFF) * (1.0f / 16777216.0f);
@@ -558,7 +560,8 @@ extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream) {
   a.tokens = h->tokens; a.n_tokens = h->n_tokens; a.w_in = h->w_in; a.w_out = h->w_out;
   a.dim = h->dim; a.ld = h->ld; a.window = h->window; a.negative = h->negative; a.lr = h->lr;
   a.alias_prob = h->alias_prob; a.alias_idx = h->alias_idx; a.vocab = h->vocab;
-  a.neg_pool = h->neg_pool; a.neg_pool_size = h->neg_pool_size; a.map_in = h->map_in;
+  a.neg_pool = h->neg_pool; a.neg_pool_size = h->neg_pool_size; a.neg_pool_size_ptr = h->neg_pool_size_ptr;
+  a.map_in = h->map_in;
   a.map_out = h->map_out; a.seed = h->seed; a.loss_sum = h->loss_sum; a.pair_count = h->pair_count;
   a.scale_in = h->scale_in; a.scale_out = h->scale_out;
   a.row_bytes = h->dim * 4;

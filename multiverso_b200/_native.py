@@ -91,7 +91,23 @@ class Sgns(C.Structure):
         ("neg_pool_size", C.c_int), ("hs_points", vp), ("hs_codes", vp), ("hs_len", vp),
         ("hs_max_code", C.c_int), ("map_in", vp), ("map_out", vp), ("seed", C.c_uint64),
         ("loss_sum", vp), ("pair_count", vp), ("variant", C.c_int), ("max_ctas", C.c_int),
-        ("scale_in", vp), ("scale_out", vp),
+        ("scale_in", vp), ("scale_out", vp), ("neg_pool_size_ptr", vp),
+    ]
+
+
+class RowBox(C.Structure):
+    _fields_ = [
+        ("map", RowMap), ("me", C.c_int), ("cap", i64), ("slot_bytes", i64), ("box", VP8), ("ack", VP8),
+        ("seg", vp), ("done", vp), ("applied", vp), ("go", vp), ("err_flag", vp), ("timeout_s", C.c_double),
+    ]
+
+
+class WePrep(C.Structure):
+    _fields_ = [
+        ("tokens", vp), ("n_tokens", i64), ("vocab", C.c_int), ("negative", C.c_int),
+        ("alias_prob", vp), ("alias_idx", vp), ("seed", C.c_uint64), ("bm_in", vp), ("bm_out", vp),
+        ("chunk_sums", vp), ("map_in", vp), ("map_out", vp), ("ids_in", vp), ("ids_out", vp),
+        ("neg_pool", vp), ("pool_cap", i64), ("counts", vp), ("cap_in", i64), ("cap_out", i64),
     ]
 
 

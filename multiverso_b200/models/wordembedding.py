@@ -12,9 +12,12 @@ B200 mapping
 * ``world == 1``: the shard *is* the table, so the block protocol degenerates exactly
   ((trained - cur)/1 added back == trained) and the K7 kernel trains in place on the HBM
   resident shards -- no gather, no scatter.
-* ``world > 1`` (block mode = reference semantics): device-side PrepareData (unique input
-  rows + negative pool), K4 row gather of the needed rows over NVLink into a local block
-  cache, K7 on the cache through id->slot maps, K3 scatter-add of (new - old)/W.
+* ``world > 1`` (block mode = reference semantics): device-side PrepareData (``mvb_we_prepare``:
+  bitmap-unique + prefix sum + negative pool, counts stay on the device), bulk-engine row pull of
+  the needed rows over NVLink into a local block cache (``mvb_rows_pull_bulk``), K7 on the cache
+  through id->slot maps, bulk-engine push of (new - old)/W (``mvb_rows_push_delta_bulk``).  No
+  host synchronisation and no eager PyTorch op anywhere in the step; pipelined, the pull of block
+  i+1 and the push of block i-1 run on a few reserved SMs under block i's K7.
 * learning-rate decay follows UpdateLearningRate (wordembedding.cpp:38-47) from the global
   word count kept in the KV table (constant.h: kWordCountId).
 """
@@ -147,6 +150,23 @@ class WordEmbedding:
         self.kernel_launches = 0
         self.kernel_variant = 0     # 0 auto | 1,2,3,5 register kernel | 10 TMA pipeline (pair at a time) | 20 window-batched
         self.max_ctas = 0           # > 0: cap K7's persistent grid (SMs left to the row pull / push kernels)
+        # pull / push kernels of the block protocol (world > 1):
+        #   "lsu" (default)   register-path pull + one-sided red.add push: 128-thread CTAs with <= 56 registers and no
+        #                     shared memory, co-resident with the persistent K7 CTA on every SM (measured at 2 GPUs:
+        #                     pull 2.2 ms + push 2.1 ms under a 9.7 ms K7, 0.96 weak-scaling efficiency)
+        #   "mbox"            register-path pull + row-mailbox push with owner-side apply (rowbox.cu; what the
+        #                     stateful updaters need -- 3x the memory traffic for the plain-add updater)
+        #   "bulk"            bulk-copy engine on `side_ctas` SMs reserved from K7's grid (op-rate bound:
+        #                     ~27 M bulk ops/s per SM)
+        self.side_mode = os.environ.get("MVB_WE_SIDE_MODE", "lsu")
+        self.side_ctas = int(os.environ.get("MVB_WE_SIDE_CTAS", "10" if self.side_mode == "bulk" else "1"))
+        if self.side_mode == "mbox" and rt.size > 1 and self._dev_block_ok() and self.input_table.S == rt.size:
+            self.input_table.enable_row_mailbox()          # collective
+            self.output_table.enable_row_mailbox()
+        elif self.side_mode == "mbox":
+            self.side_mode = "lsu"
+        self.num_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        self._bufs = [None, None]   # device-side block protocol: two buffer sets (block i trains, i+1 is pulled)
         self.scale_in = self.scale_out = None
         self._build_hot_row_cap()
 
@@ -192,7 +212,7 @@ class WordEmbedding:
 
     # ------------------------------------------------------------------ K7 launch
     def _launch(self, tokens: torch.Tensor, w_in, w_out, g2_in, g2_out, ld, map_in=None,
-                map_out=None, neg_pool=None, compute_loss=True) -> None:
+                map_out=None, neg_pool=None, compute_loss=True, neg_pool_size_ptr=None, max_ctas=None) -> None:
         o = self.opt
         a = N.Sgns()
         a.tokens, a.n_tokens = tokens.data_ptr(), tokens.numel()
@@ -208,6 +228,7 @@ class WordEmbedding:
         a.vocab = self.V
         a.neg_pool = N.ptr(neg_pool)
         a.neg_pool_size = neg_pool.numel() if neg_pool is not None else 0
+        a.neg_pool_size_ptr = N.ptr(neg_pool_size_ptr)
         if self.huffman is not None:
             a.hs_points, a.hs_codes = self.huffman.points.data_ptr(), self.huffman.codes.data_ptr()
             a.hs_len, a.hs_max_code = self.huffman.lens.data_ptr(), self.huffman.max_code
@@ -217,7 +238,7 @@ class WordEmbedding:
         a.loss_sum = self.loss.data_ptr() if compute_loss else None
         a.pair_count = self.pairs.data_ptr()
         a.variant = self.kernel_variant
-        a.max_ctas = self.max_ctas
+        a.max_ctas = self.max_ctas if max_ctas is None else max_ctas
         a.scale_in, a.scale_out = N.ptr(self.scale_in), N.ptr(self.scale_out)
         N.check(N.cuda_lib().mvb_sgns_train(C.byref(a), C.c_void_p(N.stream_ptr())), "mvb_sgns_train")
         self.kernel_launches += 1
@@ -261,7 +282,7 @@ class WordEmbedding:
             self._record_streams(st, main)
         inputs_ready = torch.cuda.Event()
         inputs_ready.record(main)                                 # next_tokens (e.g. an H2D copy) is complete here
-        self._train_prepared(tokens, st, compute_loss)
+        self._train_prepared(tokens, st, compute_loss, pipelined=True)
         trained = torch.cuda.Event()
         trained.record(main)
         with torch.cuda.stream(side):
@@ -273,11 +294,13 @@ class WordEmbedding:
                 nxt["ready"].record(side)
                 self._prefetched = nxt
             side.wait_event(trained)
-            self._add_delta(st)
+            self._add_delta(st, side=True)
         self._pending_side = True
 
     @staticmethod
     def _record_streams(st: dict, stream) -> None:
+        if st.get("dev"):
+            return                      # persistent buffers: never handed back to the caching allocator
         for v in st.values():
             if isinstance(v, torch.Tensor):
                 v.record_stream(stream)
@@ -288,8 +311,101 @@ class WordEmbedding:
             torch.cuda.current_stream().wait_stream(self._side)
             self._pending_side = False
 
+    # ------------------------------------------------------------------ device-side block protocol
+    def _dev_block_ok(self) -> bool:
+        o = self.opt
+        if os.environ.get("MVB_WE_DEV_BLOCK", "1") == "0":
+            return False
+        return (not o.hs and not o.cbow and not o.use_adagrad and o.negative_num >= 1 and o.negative_num <= 7
+                and self.D % 4 == 0 and self.LD % 4 == 0 and self.kernel_variant in (0, 20))
+
+    def _block_buffers(self, slot: int, n_tokens: int) -> dict:
+        """Fixed-capacity buffers of one in-flight block: nothing is allocated or sized on the host per
+        block (the counts only exist on the device)."""
+        b = self._bufs[slot]
+        cap_in = min(self.V, max(int(n_tokens), 1))
+        if b is not None and b["cap_in"] >= cap_in:
+            return b
+        o, dev, V, LD = self.opt, self.dev, self.V, self.LD
+        cap_out = min(V, cap_in * (1 + o.negative_num))
+        words = (V + 31) // 32
+        i32 = dict(dtype=torch.int32, device=dev)
+        b = dict(cap_in=cap_in, cap_out=cap_out, dev=True,
+                 bm_in=torch.empty(words, **i32), bm_out=torch.empty(words, **i32),
+                 chunk_sums=torch.empty((words + 1023) // 1024 + 1, **i32),
+                 map_in=torch.empty(V, **i32), map_out=torch.empty(V, **i32),
+                 ids_in=torch.empty(cap_in, **i32), ids_out=torch.empty(cap_out, **i32),
+                 neg_pool=torch.empty(max(cap_in * o.negative_num, 1), **i32), counts=torch.zeros(4, **i32),
+                 cache_in=torch.empty(cap_in, LD, device=dev), old_in=torch.empty(cap_in, LD, device=dev),
+                 cache_out=torch.empty(cap_out, LD, device=dev), old_out=torch.empty(cap_out, LD, device=dev))
+        b["n_pool"] = b["counts"][2:]
+        self._bufs[slot] = b
+        return b
+
+    def _prepare_block_dev(self, tokens: torch.Tensor, side: bool) -> dict:
+        """PrepareData + RequestParameter, entirely enqueued on the current stream."""
+        slot = self._map_slot
+        self._map_slot ^= 1
+        b = self._block_buffers(slot, tokens.numel())
+        o, lib = self.opt, N.cuda_lib()
+        st = C.c_void_p(N.stream_ptr())
+        self._step += 1
+        p = N.WePrep()
+        p.tokens, p.n_tokens, p.vocab, p.negative = tokens.data_ptr(), tokens.numel(), self.V, o.negative_num
+        p.alias_prob, p.alias_idx = N.ptr(self.alias_prob), N.ptr(self.alias_idx)
+        p.seed = ((0xA24BAED4963EE407 * (self.rt.rank + 1)) ^ (self._step * 0x9FB21C651E98DF25)) & 0xFFFFFFFFFFFFFFFF
+        p.bm_in, p.bm_out, p.chunk_sums = b["bm_in"].data_ptr(), b["bm_out"].data_ptr(), b["chunk_sums"].data_ptr()
+        p.map_in, p.map_out = b["map_in"].data_ptr(), b["map_out"].data_ptr()
+        p.ids_in, p.ids_out = b["ids_in"].data_ptr(), b["ids_out"].data_ptr()
+        p.neg_pool, p.pool_cap, p.counts = b["neg_pool"].data_ptr(), b["neg_pool"].numel(), b["counts"].data_ptr()
+        p.cap_in, p.cap_out = b["cap_in"], b["cap_out"]
+        with monitor("WE_PREPARE_DATA", cuda=True):
+            N.check(lib.mvb_we_prepare(C.byref(p), st), "mvb_we_prepare")
+        self.kernel_launches += int(lib.mvb_we_prepare_launches(C.c_int(o.negative_num)))
+        ctas = (self.side_ctas if self.side_mode == "bulk" else -self.side_ctas) if side else 32
+        cnt = b["counts"].data_ptr()
+        with monitor("WE_REQUEST_PARAMETER", cuda=True):
+            for tab, ids, ci, cache, old, cap in ((self.input_table, b["ids_in"], 0, b["cache_in"], b["old_in"], b["cap_in"]),
+                                                  (self.output_table, b["ids_out"], 1, b["cache_out"], b["old_out"], b["cap_out"])):
+                N.check(lib.mvb_rows_pull_bulk(C.byref(tab._rowmap), C.c_int(4), C.c_void_p(ids.data_ptr()),
+                                               C.c_void_p(cnt + 4 * ci), C.c_int64(cap), C.c_void_p(cache.data_ptr()),
+                                               C.c_void_p(old.data_ptr()), C.c_int64(self.LD), C.c_int(ctas), st),
+                        "mvb_rows_pull_bulk")
+        self.kernel_launches += 2
+        return b
+
+    def _add_delta_dev(self, b: dict, side: bool) -> None:
+        """AddDeltaParameter (communicator.cpp:206-249): rows += (trained - pulled) / W, pushed one-sided."""
+        lib, st = N.cuda_lib(), C.c_void_p(N.stream_ptr())
+        cnt = b["counts"].data_ptr()
+        if self.side_mode == "mbox":
+            cur = torch.cuda.current_stream()
+            with monitor("WE_ADD_DELTA", cuda=True):
+                for tab, ids, ci, cache, old, cap in ((self.input_table, b["ids_in"], 0, b["cache_in"], b["old_in"], b["cap_in"]),
+                                                      (self.output_table, b["ids_out"], 1, b["cache_out"], b["old_out"], b["cap_out"])):
+                    tab._mailbox.push_delta(ids, cnt + 4 * ci, cap, cache, old, 1.0 / self.W, ctas_per_sm=self.side_ctas)
+                    self.kernel_launches += 2
+            with monitor("WE_APPLY_DELTA", cuda=True):
+                # serve my shards: whatever the other workers have pushed by now (async PS: no waiting)
+                for tab in (self.input_table, self.output_table):
+                    tab._mailbox.drain(wait=False, ctas_per_sm=self.side_ctas, stream=cur)
+                    self.kernel_launches += tab._mailbox.launches_per_drain()
+            return
+        ctas = (self.side_ctas if self.side_mode == "bulk" else -self.side_ctas) if side else 32
+        with monitor("WE_ADD_DELTA", cuda=True):
+            for tab, ids, ci, cache, old, cap in ((self.input_table, b["ids_in"], 0, b["cache_in"], b["old_in"], b["cap_in"]),
+                                                  (self.output_table, b["ids_out"], 1, b["cache_out"], b["old_out"], b["cap_out"])):
+                N.check(lib.mvb_rows_push_delta_bulk(C.byref(tab._rowmap), C.c_void_p(ids.data_ptr()),
+                                                     C.c_void_p(cnt + 4 * ci), C.c_int64(cap),
+                                                     C.c_void_p(cache.data_ptr()), C.c_void_p(old.data_ptr()),
+                                                     C.c_int64(self.LD), C.c_float(1.0 / self.W), C.c_int(ctas), st),
+                        "mvb_rows_push_delta_bulk")
+        self.kernel_launches += 2
+
     def _prepare_block(self, tokens: torch.Tensor, wait: bool) -> dict:
         """PrepareData (data_block / communicator.cpp:117-155) + RequestParameter on the current stream."""
+        if self._dev_block_ok():
+            return self._prepare_block_dev(tokens, side=not wait)
         o, dev, V = self.opt, self.dev, self.V
         slot = self._map_slot
         self._map_slot ^= 1
@@ -331,13 +447,22 @@ class WordEmbedding:
             st["old_g2i"], st["old_g2o"] = st["g2i"].clone(), st["g2o"].clone()
         return st
 
-    def _train_prepared(self, tokens: torch.Tensor, st: dict, compute_loss: bool) -> None:
+    def _train_prepared(self, tokens: torch.Tensor, st: dict, compute_loss: bool, pipelined: bool = False) -> None:
         with monitor("WE_TRAIN_BLOCK", cuda=True):
-            self._launch(tokens, st["cache_in"], st["cache_out"], st["g2i"], st["g2o"], self.LD,
-                         st["map_in"], st["map_out"], st["neg_pool"], compute_loss)
+            if st.get("dev"):
+                # pipelined: leave `side_ctas` SMs to the pull / push kernels running on the side stream
+                cap = max(1, self.num_sms - self.side_ctas) if (pipelined and self.side_mode == "bulk") else None
+                self._launch(tokens, st["cache_in"], st["cache_out"], None, None, self.LD, st["map_in"], st["map_out"],
+                             st["neg_pool"], compute_loss, neg_pool_size_ptr=st["n_pool"], max_ctas=cap)
+            else:
+                self._launch(tokens, st["cache_in"], st["cache_out"], st["g2i"], st["g2o"], self.LD,
+                             st["map_in"], st["map_out"], st["neg_pool"], compute_loss)
 
-    def _add_delta(self, st: dict) -> None:
+    def _add_delta(self, st: dict, side: bool = False) -> None:
         # AddDeltaParameter (communicator.cpp:206-249): delta = (trained - pulled) / W
+        if st.get("dev"):
+            self._add_delta_dev(st, side)
+            return
         o, D = self.opt, self.LD
         inv = 1.0 / self.W
         in_ids, out_ids = st["in_ids"], st["out_ids"]
@@ -365,7 +490,9 @@ class WordEmbedding:
 
     # ------------------------------------------------------------------ results
     def embeddings(self) -> torch.Tensor:
-        """Whole input-embedding matrix [V, D] (SaveEmbedding pulls it in 100k-row batches)."""
+        """Whole input-embedding matrix [V, D] (SaveEmbedding pulls it in 100k-row batches).  With the
+        row mailboxes a worker's last deltas are applied by their owners at the next MV_Barrier (the
+        reference's SaveEmbedding is preceded by one, distributed_wordembedding.cpp:232-237)."""
         self.flush()
         return self.input_table.get().view(self.V, self.LD)[:, :self.D]
 

@@ -167,6 +167,7 @@ class Runtime:
         self._gloo = None
         self.pads: Optional[SymmBuffer] = None
         self.err_flag = None
+        self.barrier_hooks = []      # callables(final: bool): served while a barrier waits (row-mailbox drains)
         self._epochs: Dict[int, int] = {}
         self._next_channel = 4       # channels 0..3 reserved (barrier, aggregate)
         self._symm: List[SymmBuffer] = []
@@ -412,6 +413,24 @@ class Runtime:
                                     C.c_void_p(self.err_flag.data_ptr()),
                                     C.c_double(float(FLAGS.get("barrier_timeout_s"))),
                                     C.c_void_p(N.stream_ptr())), "mvb_barrier")
+            if self.barrier_hooks:
+                # Row mailboxes: a rank waiting here still serves the pushes of the ranks that have not
+                # arrived yet (they may be spinning for its ack), then -- every rank has rung its doorbells
+                # before it entered -- applies what is left and meets the others once more.
+                import time
+                ev = torch.cuda.Event()
+                ev.record()
+                while not ev.query():
+                    for h in self.barrier_hooks:
+                        h(False)
+                    time.sleep(2e-4)
+                for h in self.barrier_hooks:
+                    h(True)
+                ep = self.next_epoch(0)
+                N.check(lib.mvb_barrier(self.pads_array(), self.rank, self.size, 0, C.c_uint64(ep),
+                                        C.c_void_p(self.err_flag.data_ptr()),
+                                        C.c_double(float(FLAGS.get("barrier_timeout_s"))),
+                                        C.c_void_p(N.stream_ptr())), "mvb_barrier")
             torch.cuda.current_stream().synchronize()
             self.check_watchdog()
         else:

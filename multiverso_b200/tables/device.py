@@ -402,6 +402,97 @@ class DenseDeviceTable(_AsyncOps):
                 st.copy_(torch.from_numpy(np.frombuffer(raw, dtype=npdt).copy()).to(self.rt.device))
 
 
+class RowMailbox:
+    """Row mailboxes of one fp32 matrix table (csrc/cuda/rowbox.cu): the device-side row Add with
+    owner-side apply.  One slot per (owner, source) in the owner's HBM, doorbell + ack flags in
+    symmetric memory.  ``push_*`` is one-sided and asynchronous; ``drain`` applies, on the owner,
+    every push that has arrived (``wait=True``: the next push of every source) through the table's
+    updater with the SOURCE's AddOption -- exactly once per (worker,row), no host barrier, workers
+    may push different numbers of times (reference: Server::ProcessAdd, src/server.cpp:48-58).
+
+    Construction is collective (symmetric allocation); everything afterwards is not."""
+
+    def __init__(self, table: "MatrixDeviceTable"):
+        rt = table.rt
+        assert table.dtype == torch.float32 and table.num_col % 4 == 0
+        assert table.S == rt.size and table.W == rt.size, "row mailboxes need every rank to be worker + server"
+        self.t, self.rt = table, rt
+        S = table.S
+        self.cap = max(hi - lo for lo, hi in zip(table.row_lo, table.row_hi))
+        lib = N.cuda_lib()
+        lib.mvb_rowbox_slot_bytes.restype = C.c_int64
+        self.slot_bytes = int(lib.mvb_rowbox_slot_bytes(C.c_int64(self.cap), C.c_int64(table.num_col)))
+        self.slot_bytes = (self.slot_bytes + 255) // 256 * 256
+        self.nslots = int(lib.mvb_rowbox_slots())
+        self.box = rt.alloc_symm(S * self.nslots * self.slot_bytes)
+        self.ack = rt.alloc_symm(8 * N.MAX_RANKS)
+        self.box.tensor(torch.uint8)[:].view(S * self.nslots, self.slot_bytes)[:, :128].zero_()   # headers: seq = 0
+        self.ack.tensor(torch.int64).zero_()
+        dev = rt.device
+        self.seg = torch.zeros(S + 1, dtype=torch.int32, device=dev)
+        self.done = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.applied = torch.zeros(S, dtype=torch.int64, device=dev)
+        self.go = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.epoch = 0                       # my pushes so far
+        self.drain_stream = torch.cuda.Stream(device=dev)
+        b = N.RowBox()
+        b.map = table._rowmap
+        b.me, b.cap, b.slot_bytes = rt.rank, self.cap, self.slot_bytes
+        b.box, b.ack = self.box.ptr_array(), self.ack.ptr_array()
+        b.seg, b.done = self.seg.data_ptr(), self.done.data_ptr()
+        b.applied, b.go = self.applied.data_ptr(), self.go.data_ptr()
+        b.err_flag = rt.err_flag.data_ptr()
+        b.timeout_s = float(FLAGS.get("barrier_timeout_s"))
+        self.c = b
+        torch.cuda.synchronize()
+        rt.barrier()
+        rt.barrier_hooks.append(self._barrier_hook)
+
+    def _barrier_hook(self, final: bool) -> None:
+        # final: every rank's pushes are complete (they synchronised their streams before the barrier):
+        # one more drain applies the at most one outstanding push per source, and the host waits for it
+        for _ in range(self.nslots if final else 1):       # at most `nslots` outstanding pushes per source
+            self.drain(wait=False)
+        if final:
+            self.drain_stream.synchronize()
+
+    def push_delta(self, ids32: torch.Tensor, n_ptr: int, n_max: int, cur: torch.Tensor, old: torch.Tensor,
+                   scale: float, option: Optional[AddOption] = None, ctas_per_sm: int = 1) -> None:
+        """rows[ids] += (cur - old) * scale at their owners (ids ascending int32; count read on the device)."""
+        self.epoch += 1
+        ao = _opt_struct(option or AddOption())
+        N.check(N.cuda_lib().mvb_rowbox_push_delta(
+            C.byref(self.c), C.c_void_p(ids32.data_ptr()), C.c_void_p(n_ptr), C.c_int64(n_max),
+            C.c_void_p(cur.data_ptr()), C.c_void_p(old.data_ptr()), C.c_int64(cur.stride(0)), C.c_float(scale),
+            C.c_uint64(self.epoch), C.byref(ao), C.c_int(ctas_per_sm), C.c_void_p(N.stream_ptr())),
+            "mvb_rowbox_push_delta")
+
+    def push_vals(self, ids32: torch.Tensor, vals: torch.Tensor, option: Optional[AddOption] = None,
+                  scale: float = 1.0, ctas_per_sm: int = 1) -> None:
+        self.epoch += 1
+        ao = _opt_struct(option or AddOption())
+        N.check(N.cuda_lib().mvb_rowbox_push_vals(
+            C.byref(self.c), C.c_void_p(ids32.data_ptr()), C.c_void_p(0), C.c_int64(ids32.numel()),
+            C.c_void_p(vals.data_ptr()), C.c_int64(vals.stride(0)), C.c_float(scale), C.c_uint64(self.epoch),
+            C.byref(ao), C.c_int(ctas_per_sm), C.c_void_p(N.stream_ptr())), "mvb_rowbox_push_vals")
+
+    def drain(self, wait: bool = False, ctas_per_sm: int = 1, stream=None) -> None:
+        """Owner side: apply what has arrived (wait=False) or the next push of every source (wait=True).
+        Enqueued on ``stream`` (default: the mailbox's own drain stream, so that a push spinning for an
+        ack on the caller's stream can never block the drain that produces the peer's ack)."""
+        t, lib = self.t, N.cuda_lib()
+        st = stream if stream is not None else self.drain_stream
+        sp = C.c_void_p(st.cuda_stream)
+        N.check(lib.mvb_rowbox_poll(C.byref(self.c), C.c_int(-1), C.c_int(1 if wait else 0), sp), "mvb_rowbox_poll")
+        for w in range(t.S):
+            N.check(lib.mvb_rowbox_apply(C.byref(self.c), C.c_int(t.updater), C.c_void_p(t.shard_buf.local_ptr),
+                                         t._sp(0), t._sp(1), C.c_int64(t.state_stride), C.c_int64(t.row_lo[t.sid]),
+                                         C.c_int(w), C.c_int(ctas_per_sm), sp), "mvb_rowbox_apply")
+
+    def launches_per_drain(self) -> int:
+        return 1 + self.t.S
+
+
 class ArrayDeviceTable(DenseDeviceTable):
     """ArrayTable<T>: dense 1-D, whole-table ops (any size >= 1)."""
 
@@ -434,6 +525,13 @@ class MatrixDeviceTable(DenseDeviceTable):
         self._rowmap.rows_per_server = self.rps
         for s in range(self.S):
             self._rowmap.shard_ptrs[s] = self.shard_ptrs[s]
+        self._mailbox = None
+        # async + stateful updater: row Adds go through the row mailboxes (owner-side apply on the device,
+        # one-sided, no lockstep).  Collective allocation, hence decided here, at table creation.
+        if (rt.size > 1 and not self.sync and self.updater not in (N.UPD_DEFAULT, N.UPD_SGD)
+                and self.dtype == torch.float32 and self.num_col % 4 == 0 and self.S == rt.size and self.W == rt.size
+                and str(FLAGS.get("row_mailbox")).lower() not in ("0", "false")):
+            self.enable_row_mailbox()
         self._stale = None
         if self.is_sparse:
             nslots = self.W * (2 if self.is_pipeline else 1)
@@ -445,7 +543,30 @@ class MatrixDeviceTable(DenseDeviceTable):
             self._nslots = nslots
             rt.barrier()
 
-    # ---- ids helper --------------------------------------------------------------------
+    def enable_row_mailbox(self) -> "RowMailbox":
+        """Collective: allocate the row mailboxes of this table (idempotent)."""
+        if self._mailbox is None:
+            self._mailbox = RowMailbox(self)
+        return self._mailbox
+
+    def drain_rows(self, wait: bool = False) -> None:
+        """Owner side of the mailbox protocol: apply the row Adds that have arrived from any worker."""
+        if self._mailbox is not None:
+            self._mailbox.drain(wait=wait)
+
+    def wait(self, handle: int) -> None:
+        if self._mailbox is None:
+            return super().wait(handle)
+        # a push may be spinning for a peer's ack while that peer spins for mine: keep serving my
+        # mailboxes while waiting (the reference's server actor never stops either)
+        import time
+        ev = self._events.pop(handle, None)
+        while ev is not None and not ev.query():
+            self._mailbox.drain(wait=False)
+            time.sleep(1e-4)
+        Runtime.get().check_watchdog()
+
+        # ---- ids helper --------------------------------------------------------------------
     def _ids(self, row_ids) -> torch.Tensor:
         t = torch.as_tensor(row_ids)
         if t.dtype != torch.int64:
@@ -534,6 +655,15 @@ class MatrixDeviceTable(DenseDeviceTable):
         workers' requests in worker order (collective, like the dense fused path)."""
         rt, lib = self.rt, N.cuda_lib()
         k = ids.numel()
+        if self._mailbox is not None:
+            # device-side path: sort by row id (the owner segments are contiguous ranges of the sorted
+            # list), one-sided push into the owners' mailboxes, then serve my own mailboxes
+            order = torch.argsort(ids)
+            ids32 = ids[order].to(torch.int32)
+            self._mailbox.push_vals(ids32, vals[order].contiguous(), opt)
+            self._keep_push = (ids32,)
+            self._mailbox.drain(wait=False)
+            return
         st = C.c_void_p(N.stream_ptr())
         ao = _opt_struct(opt)
         if rt.size == 1:

@@ -117,9 +117,35 @@ def scenario_async():
     ma = mv.MatrixTable(512, 32, "float32", updater="adagrad")
     rid = torch.arange(0, 512, 3, device="cuda")
     ma.add_rows(rid, torch.ones(rid.numel(), 32, device="cuda") * 0.01, mv.AddOption(learning_rate=0.01, rho=0.1))
+    mv.barrier()                       # row mailboxes: pushes are applied by their owners, at the latest here
     got = ma.get().view(512, 32)
     # each worker has its own G^2 history: g=1, G2=1 -> step = rho/sqrt(1+1e-6)
     check("stateful_rows_adagrad", torch.allclose(got[rid], torch.full((rid.numel(), 32), -0.1 * W, device="cuda"), atol=1e-4))
+    # device-side mailboxes: workers are NOT in lockstep -- rank r issues r+1 row Adds (unsorted ids, rows of
+    # every owner), per-worker learning rates travel with the push; per-worker AdaGrad history makes the
+    # result exact: the k-th add of a worker moves its rows by rho / sqrt(k)
+    mu = mv.MatrixTable(3001, 64, "float32", updater="adagrad")
+    check("row_mailbox_enabled", (mu._mailbox is not None) == (W > 1))
+    urid = torch.randperm(3001, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))[:1500]
+    for k in range(r + 1):
+        lr_w = 0.01 * (r + 1)
+        mu.add_rows(urid, torch.full((1500, 64), lr_w, device="cuda"), mv.AddOption(learning_rate=lr_w, rho=0.1))
+    mv.barrier()
+    exp_u = -sum(0.1 / (k ** 0.5) for w in range(W) for k in range(1, 2 + w))
+    gu = mu.get().view(3001, 64)
+    untouched = torch.ones(3001, dtype=torch.bool, device="cuda"); untouched[urid] = False
+    check("stateful_rows_uneven_mailbox", torch.allclose(gu[urid], torch.full((1500, 64), exp_u, device="cuda"), rtol=1e-4)
+          and bool((gu[untouched] == 0).all()), f"{gu[urid][0, :2].tolist()} vs {exp_u}")
+    # momentum (shared state): one push per worker, applied sequentially by the owner -> order-independent only
+    # for equal deltas: s = m s + (1-m) g applied W times to rows that start at 0
+    mm = mv.MatrixTable(1000, 32, "float32", updater="momentum_sgd")
+    mm.add_rows(torch.arange(0, 1000, 2, device="cuda"), torch.ones(500, 32, device="cuda"), mv.AddOption(momentum=0.5))
+    mv.barrier()
+    sm, dm = 0.0, 0.0
+    for w in range(W):
+        sm = 0.5 * sm + 0.5 * 1.0
+        dm -= sm
+    check("stateful_rows_momentum_mailbox", torch.allclose(mm.get().view(1000, 32)[::2], torch.full((500, 32), dm, device="cuda"), rtol=1e-5))
     # KV
     kv = mv.KVTable("int64", "float32")
     keys = torch.arange(0, 1000, device="cuda")
@@ -189,6 +215,34 @@ def scenario_async():
         ref2 = x2.double() @ W2.double().T
         err2 = (y2.double() - ref2).abs().max().item()
         check(f"get_gemm_peer_scratch_M{Mrows}", err2 < 4e-3 * 18 * 4, str(err2))
+    mv.barrier()
+    # device-side block protocol across ranks: bulk-engine pull from peer shards, one-sided delta push
+    import ctypes as C
+    from multiverso_b200 import _native as N
+    bt = mv.MatrixTable(40000, 300, "float32", min_value=-1.0, max_value=1.0, seed=11)
+    mv.barrier()
+    bfull = bt.get().view(40000, 300).clone()
+    bids = torch.arange(r, 40000, 3, device="cuda", dtype=torch.int32)          # rows of every owner
+    kk = bids.numel()
+    ndev = torch.tensor([kk], dtype=torch.int32, device="cuda")
+    cache = torch.zeros(kk + 7, 300, device="cuda"); old = torch.zeros(kk + 7, 300, device="cuda")
+    lib, stp = N.cuda_lib(), C.c_void_p(N.stream_ptr())
+    N.check(lib.mvb_rows_pull_bulk(C.byref(bt._rowmap), C.c_int(4), C.c_void_p(bids.data_ptr()), C.c_void_p(ndev.data_ptr()),
+                                   C.c_int64(kk + 7), C.c_void_p(cache.data_ptr()), C.c_void_p(old.data_ptr()),
+                                   C.c_int64(300), C.c_int(6), stp), "pull")
+    torch.cuda.synchronize()
+    check("rows_pull_bulk_peer", torch.equal(cache[:kk], bfull[bids.long()]) and torch.equal(old[:kk], bfull[bids.long()]))
+    mv.barrier()
+    cache[:kk] += float(r + 1)
+    N.check(lib.mvb_rows_push_delta_bulk(C.byref(bt._rowmap), C.c_void_p(bids.data_ptr()), C.c_void_p(ndev.data_ptr()),
+                                         C.c_int64(kk + 7), C.c_void_p(cache.data_ptr()), C.c_void_p(old.data_ptr()),
+                                         C.c_int64(300), C.c_float(0.5), C.c_int(6), stp), "push")
+    torch.cuda.synchronize()
+    mv.barrier()
+    bexp = bfull.clone()
+    for w in range(W):
+        bexp[torch.arange(w, 40000, 3, device="cuda")] += 0.5 * (w + 1)
+    check("rows_push_delta_bulk_peer", torch.allclose(bt.get().view(40000, 300), bexp, rtol=0, atol=1e-5))
     mv.barrier()
     # distributed WordEmbedding block (block mode)
     from multiverso_b200.models.wordembedding import WordEmbedding, WordEmbeddingOption, synthetic_zipf_corpus

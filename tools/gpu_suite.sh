@@ -97,6 +97,17 @@ cap)
   done
   done
   ;;
+blk)
+  # round 2: device-side block protocol: 1-GPU kernel tests, then (NG>1) multi-GPU scenarios + bench
+  timeout 600 python -m pytest tests/test_gpu_we_block.py tests/test_gpu_wordembedding.py -x -q > gpurun_out/pytest_blk.log 2>&1; echo "pytest blk rc=$?"; tail -6 gpurun_out/pytest_blk.log
+  if [ "$NG" -gt 1 ]; then
+    timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $PORT tests/mp_device_check.py async > gpurun_out/mp_check_async.log 2>&1; echo "mp async rc=$?"; grep -E "PASS|FAIL|Error|error" gpurun_out/mp_check_async.log | head -12
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+1)) bench.py --gpus $NG --steps 10 --warmup 3 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err; echo "bench$NG rc=$?"; cut -c1-1500 gpurun_out/bench_n$NG.json; tail -5 gpurun_out/bench_n$NG.err
+    for sc in ${SIDE_CTAS:-}; do
+      MVB_WE_SIDE_MODE=${SIDE_MODE:-bulk} MVB_WE_SIDE_CTAS=$sc timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+2)) bench.py --gpus $NG --steps 10 --warmup 3 --no-table-bw > gpurun_out/bench_n${NG}_side$sc.json 2> gpurun_out/bench_n${NG}_side$sc.err; echo "bench$NG side=$sc rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_n${NG}_side$sc.json'));print(round(d['value']/1e6,1), round(d['e2e']['value']/1e6,1), d['config']['loss_per_pair'], {k:round(v['avg_ms'],2) for k,v in d['extra']['monitors_device_arm'].items()})"
+    done
+  fi
+  ;;
 refarm)
   timeout 1500 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_n1.json
   ;;
