@@ -105,3 +105,50 @@ def run_wordembedding(ref_bin: str, args) -> dict:
                 "note": "CPU program reading its corpus from disk: the number is end to end by construction"},
         "gpu_launches": 0,
     }
+
+
+def run_matrix_bw(ref_bin: str, rows: int = 1_000_000, cols: int = 512, iters: int = 2) -> dict:
+    """BASELINE.json config 2 on the UNMODIFIED reference: MatrixTable rows x cols fp32, whole-table Add
+    (server-side sgd updater) and whole-table Get through the reference's public C++ API
+    (baseline/ref_matrix_bw_main.cpp, the calls of Test/test_matrix_perf.cpp), one process per rank over
+    the MPI shim.  Table bytes / wall time, max over ranks."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    work = os.environ.get("MV_REF_WORKDIR", "/tmp/mv_ref_arm")
+    os.makedirs(work, exist_ok=True)
+    threads = max(1, (os.cpu_count() or 8) // world)
+    env = dict(os.environ, MV_SHIM_RANK=str(rank), MV_SHIM_SIZE=str(world), OMP_NUM_THREADS=str(threads))
+    p = subprocess.run([ref_bin, str(rows), str(cols), str(iters), f"-omp_threads={min(threads, 64)}"],
+                       capture_output=True, text=True, env=env, cwd=work, timeout=1700)
+    mine = None
+    for line in p.stdout.splitlines():
+        if line.startswith("{"):
+            mine = json.loads(line)
+    if p.returncode != 0 or mine is None:
+        raise RuntimeError(f"reference matrix_bw rc={p.returncode}: {(p.stdout + p.stderr)[-300:]}")
+    with open(os.path.join(work, f"bw_result_{rank}.json"), "w") as f:
+        json.dump(mine, f)
+    if rank != 0:
+        return {"impl": "reference", "rank": rank, "note": "aggregated by rank 0"}
+    results = [mine]
+    deadline = time.time() + 1800
+    for r in range(1, world):
+        path = os.path.join(work, f"bw_result_{r}.json")
+        while not os.path.exists(path) and time.time() < deadline:
+            time.sleep(0.2)
+        time.sleep(0.05)
+        results.append(json.load(open(path)))
+    for r in range(world):
+        try:
+            os.remove(os.path.join(work, f"bw_result_{r}.json"))
+        except OSError:
+            pass
+    add_ms = max(x["add_ms"] for x in results)
+    get_ms = max(x["get_ms"] for x in results)
+    nbytes = rows * cols * 4
+    return {"metric": "matrix_table_get_plus_add_gbs", "value": 2 * nbytes / (add_ms + get_ms) / 1e6, "unit": "GB/s",
+            "higher_is_better": True, "add_ms": add_ms, "get_ms": get_ms, "add_gbs": nbytes / add_ms / 1e6,
+            "get_gbs": nbytes / get_ms / 1e6, "iters": iters, "verified": all(x["verified"] for x in results),
+            "config": {"table": f"MatrixTable {rows}x{cols} fp32, whole-table Add (sgd updater) + whole-table Get",
+                       "parallelism": f"{world} CPU process(es) x {threads} threads, reference PS over the MPI shim",
+                       "timing": "reference Timer (wall clock) around blocking Add / Get, max over ranks"}}

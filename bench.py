@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--negative", type=int, default=5)
     ap.add_argument("--window", type=int, default=5)
     ap.add_argument("--no-table-bw", action="store_true", help="skip the MatrixTable Get/Add sweep")
+    ap.add_argument("--metric", default="words", choices=["words", "matrix_bw"],
+                    help="words: WordEmbedding words/s (+ MatrixTable Get+Add GB/s as `secondary`); "
+                         "matrix_bw: only the MatrixTable 1Mx512 Get+Add GB/s line (BASELINE.json config 2)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="world > 1: train / pull / push strictly one after the other (-is_pipeline 0)")
     return ap.parse_args()
@@ -190,6 +193,10 @@ def main():
     rank = mv.rank()
     dev = torch.device("cuda", torch.cuda.current_device())
     K, W, B = args.steps, max(args.warmup, 3), args.block_words
+    if args.metric == "matrix_bw":
+        matrix_bw_main(mv, torch, world, rank, args)
+        mv.shutdown()
+        return
 
     opt = WordEmbeddingOption(embeding_size=args.dim, window_size=args.window,
                               negative_num=args.negative, init_learning_rate=0.025, sample=0.0,
@@ -327,8 +334,68 @@ def main():
             "gpu_launches": launches,
             "extra": dict(extra, monitors_device_arm=monitors, e2e_trace_rank0=e2e_trace),
         }
+        if "get_plus_add_gbs" in extra:
+            # second half of the BASELINE.json metric, same key in the reference arm's line
+            out["secondary"] = secondary_block(extra, world)
         print(json.dumps(out), flush=True)
     mv.shutdown()
+
+
+def secondary_block(extra, world):
+    return {"metric": "matrix_table_get_plus_add_gbs", "value": extra["get_plus_add_gbs"], "unit": "GB/s",
+            "higher_is_better": True, "add_ms": extra["add_ms"], "get_ms": extra["get_ms"],
+            "add_gbs": extra["add_gbs"], "get_gbs": extra["get_gbs"], "iters": 5,
+            "config": {"table": "MatrixTable 1000000x512 fp32, whole-table Add (sgd updater fused) + whole-table Get",
+                       "parallelism": f"{world} GPU(s), row-sharded, fused P2P kernels (no NCCL on the path)",
+                       "timing": "CUDA events, max over ranks; 2.05 GB table >> 126 MB L2"}}
+
+
+def matrix_bw_main(mv, torch, world, rank, args):
+    """`--metric matrix_bw`: BASELINE.json config 2 as the primary line (same JSON contract)."""
+    sampler = ClockSampler(torch.cuda.current_device(), source="nvml")
+    if rank == 0:
+        sampler.start()
+    sampler.mark_begin()
+    extra = table_bandwidth(mv, torch, world)
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end through the public API: the delta comes from pinned host memory, the pulled table goes back
+    # to pinned host memory, every iteration
+    rows, cols = 1_000_000, 512
+    e2e = None
+    try:
+        t = mv.MatrixTable(rows, cols, "float32", updater="sgd")
+        host_delta = torch.full((rows * cols,), 1e-3).pin_memory()
+        host_out = torch.empty(rows * cols).pin_memory()
+        dev_delta = torch.empty(rows * cols, device="cuda")
+        dev_out = torch.empty(rows * cols, device="cuda")
+        n = 3
+        for it in range(n + 1):
+            if it == 1:
+                torch.cuda.synchronize(); mv.barrier()
+                import time as _t
+                t0 = _t.perf_counter()
+            dev_delta.copy_(host_delta, non_blocking=True)
+            t.add(dev_delta)
+            t.get(dev_out)
+            host_out.copy_(dev_out, non_blocking=True)
+            torch.cuda.synchronize()
+        ms = torch.tensor([(_t.perf_counter() - t0) * 1e3 / n], dtype=torch.float64, device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": 2 * rows * cols * 4 / float(ms) / 1e6, "unit": "GB/s", "h2d_bytes_per_step": rows * cols * 4,
+               "d2h_bytes_per_step": rows * cols * 4, "ms_per_step": float(ms),
+               "note": "delta from pinned host memory (H2D), Add, Get, table back to pinned host memory (D2H): PCIe bound"}
+    except Exception as e:   # noqa: BLE001
+        e2e = {"error": repr(e)[:200]}
+    if rank == 0:
+        out = {"metric": "matrix_table_get_plus_add_gbs", "value": extra.get("get_plus_add_gbs"), "unit": "GB/s",
+               "n_gpus": world, "steps": 5, "warmup": 2, "ms_per_step": (extra.get("add_ms", 0) + extra.get("get_ms", 0)),
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+               "impl": "ours", "config": secondary_block(extra, world)["config"] if "get_plus_add_gbs" in extra else {},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": 14, "extra": extra}
+        print(json.dumps(out), flush=True)
 
 
 def table_bandwidth(mv, torch, world):

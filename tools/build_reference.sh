@@ -32,4 +32,8 @@ g++ -O2 -std=c++11 -c $ROOT/baseline/ref_matrix_perf_main.cpp -o $OBJ/perf_main.
 wait
 g++ -fopenmp -o $OUT/bin/matrix_perf $OBJ/core_*.o $OBJ/mpi_shim.o $OBJ/perf_test.o $OBJ/perf_main.o -lpthread -ldl \
   && echo "built $OUT/bin/matrix_perf"
+# BASELINE config 2 through the reference's public API: MatrixTable rows x cols whole-table Add / Get
+g++ $CXXFLAGS -c $ROOT/baseline/ref_matrix_bw_main.cpp -o $OBJ/bw_main.o \
+  && g++ -fopenmp -o $OUT/bin/matrix_bw $OBJ/core_*.o $OBJ/mpi_shim.o $OBJ/bw_main.o -lpthread -ldl \
+  && echo "built $OUT/bin/matrix_bw"
 rm -rf $OBJ

@@ -108,6 +108,18 @@ blk)
     done
   fi
   ;;
+r2n8)
+  # round 2, one multi-GPU call: scenarios (async + sync), headline bench, side-CTA variant, dense Get bulk experiment
+  for w in async sync; do
+    timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+20)) tests/mp_device_check.py $w > gpurun_out/mp_check_${w}_n$NG.log 2>&1; echo "mp $w rc=$?"; grep -cE "PASS" gpurun_out/mp_check_${w}_n$NG.log; grep -E "FAIL|Error|Traceback" gpurun_out/mp_check_${w}_n$NG.log | head -5 | cut -c1-600
+  done
+  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+21)) bench.py --gpus $NG --steps 20 --warmup 5 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err; echo "bench$NG rc=$?"; grep '^{' gpurun_out/bench_n$NG.json | cut -c1-1200; tail -3 gpurun_out/bench_n$NG.err
+  MVB_WE_SIDE_CTAS=2 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+22)) bench.py --gpus $NG --steps 10 --warmup 3 --no-table-bw > gpurun_out/bench_n${NG}_side2.json 2> gpurun_out/bench_n${NG}_side2.err; echo "bench$NG side2 rc=$?"
+  L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+23))"
+  for v in 0 1; do
+    MVB_GET_BULK=$v timeout 300 $L bench/matrix_bw.py > gpurun_out/matrix_bw_bulk${v}_n$NG.log 2>&1; echo "matrix_bw MVB_GET_BULK=$v rc=$?"; grep '^{' gpurun_out/matrix_bw_bulk${v}_n$NG.log | tail -1 | cut -c1-700
+  done
+  ;;
 refarm)
   timeout 1500 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_n1.json
   ;;
