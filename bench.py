@@ -265,30 +265,54 @@ def main():
     we.flush()
     sync_all()
     we._prefetched = None
+    E2E_WARM = 2                                     # untimed iterations of the SAME loop (pipeline primed)
     tok2 = [tok_dev, torch.empty_like(tok_dev)]
     loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     losses_host = []
-    if pipelined:
-        tok2[0].copy_(pinned[W], non_blocking=True)              # block 0 of the arm; each step copies the NEXT one
-        sync_all()
+    copy_stream = torch.cuda.Stream(device=dev)      # the H2D copy of block i+1 runs under block i's training
+    main_stream = torch.cuda.current_stream()
+    tok2[0].copy_(pinned[W + (-E2E_WARM) % K], non_blocking=True)      # the first warm-up block
+    copied = torch.cuda.Event()
+    copied.record()
+    sync_all()
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(we2_steps + 1)]
+    done_ev = torch.cuda.Event()                     # end of the previous iteration's work on the main stream
+    done_ev.record()
     host_t = []
     t0 = time.perf_counter()
-    step_ev[0].record()
-    for i in range(we2_steps):
+    for i in range(-E2E_WARM, we2_steps):
+        if i == 0:
+            torch.cuda.synchronize()                 # the primed pipeline (prefetched block, copied tokens) survives this
+            if world > 1:
+                mv.barrier()
+            t0 = time.perf_counter()
+            step_ev[0].record()
+            done_ev = step_ev[0]
         we.loss.zero_()
+        cur, nxt = tok2[i % 2], tok2[(i + 1) % 2]
+        cur_copied = copied
+        # H2D of one block of inputs per step: block i+1, from pinned host memory, on the copy stream; its
+        # buffer was last read by block i-1, i.e. before `done_ev`
+        copy_stream.wait_event(done_ev)
+        with torch.cuda.stream(copy_stream):
+            nxt.copy_(pinned[W + (i + 1) % K], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(copy_stream)
+        main_stream.wait_event(cur_copied)           # this step's tokens are on the device
         if pipelined:
-            nxt = tok2[(i + 1) % 2]
-            nxt.copy_(pinned[W + (i + 1) % K], non_blocking=True)    # H2D of one block of inputs per step
-            we.train_block(tok2[i % 2], compute_loss=True, next_tokens=nxt)
+            we.train_block(cur, compute_loss=True, next_tokens=nxt, next_ready=copied)
         else:
-            tok_dev.copy_(pinned[W + i], non_blocking=True)      # H2D of this step's inputs
-            we.train_block(tok_dev, compute_loss=True)
+            we.train_block(cur, compute_loss=True)
         loss_pin[i % 2].copy_(we.loss, non_blocking=True)        # D2H of the step's result
         loss_ev[i % 2].record()
-        step_ev[i + 1].record()
-        host_t.append(time.perf_counter() - t0)
+        if i >= 0:
+            step_ev[i + 1].record()
+            done_ev = step_ev[i + 1]
+            host_t.append(time.perf_counter() - t0)
+        else:
+            done_ev = torch.cuda.Event()
+            done_ev.record()
         if i > 0:                                                # consume step i-1's loss on the host
             loss_ev[(i - 1) % 2].synchronize()
             losses_host.append(float(loss_pin[(i - 1) % 2]))
@@ -329,8 +353,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "words/s", "h2d_bytes_per_step": B * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / K,
-                    "note": "H2D of a block and D2H of the loss every step; loss of step i consumed on the host "
-                            "during step i+1" + ("; the block copied in step i is step i+1's" if pipelined else "")},
+                    "note": "every step: H2D of one block of tokens from pinned host memory (copy stream, the block copied in "
+                            "step i is step i+1's) and D2H of the step's loss into pinned host memory, consumed on the host "
+                            "during step i+1; 2 untimed warm-up iterations of the same loop"},
             "gpu_launches": launches,
             "extra": dict(extra, monitors_device_arm=monitors, e2e_trace_rank0=e2e_trace),
         }

@@ -66,13 +66,19 @@ struct WinDev {
   int ring;          // input-row ring slots (>= 2*kNW + 2*window + 1)
   int nw;            // active consumer warps (<= kNW)
   int ko;            // 1 + negative
+  int chunk;         // token positions per work unit (dynamic scheduling)
+  unsigned int* ctr; // [0] next chunk, [1] CTAs that ran out of work (self-resetting)
 };
+
+// chunk tickets of the launch in flight (one K7 launch at a time per process; the last CTA resets them)
+__device__ unsigned int g_win_ctr[2];
 
 struct OutMeta {
   float* ptr[kKO];   // global row addresses (nullptr = row unused)
   float scale[kKO];  // step scale of the row (1 unless the word is in the capped Zipf head)
-  int active;        // 0 => virtual / sentence-break position: nothing to train
-  int pad[7];
+  long long p;       // token position of this centre (seeds its window shrink / negatives)
+  int active;        // 1 train, 0 virtual / sentence-break position, -1 end of work (consumer exits)
+  int pad[5];
 };
 static_assert(sizeof(OutMeta) == 128, "OutMeta size");
 
@@ -204,12 +210,12 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
   const int R = a.ring;
   const int NW = a.nw;
 
-  // contiguous token range of this CTA
-  const int64_t ra = a.n_tokens * (int64_t)blockIdx.x / gridDim.x;
-  const int64_t rb = a.n_tokens * (int64_t)(blockIdx.x + 1) / gridDim.x;
-  const int64_t len = rb - ra;
-  const int64_t nj = len + 2 * W;          // ring positions  j <-> token position ra - W + j
-  const int64_t nv = len + 4 * W;          // virtual centres i <-> token position ra - 2W + i
+  // Work units are chunks of `a.chunk` consecutive token positions handed out by an atomic counter (a CTA
+  // slowed down by co-resident row pull / push kernels simply takes fewer).  Inside a CTA the chunks form ONE
+  // stream of virtual positions G = 0, 1, 2, ...: chunk [ra, rb) contributes rb - ra + 4W of them (local index
+  // i <-> centre token ra - 2W + i, ring entry i <-> input token ra - W + i, empty beyond the chunk), so ring
+  // slots, stages and barrier phases simply continue across chunks.
+  const int64_t n_chunks = (a.n_tokens + a.chunk - 1) / a.chunk;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
@@ -223,7 +229,6 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (len <= 0) return;
 
   if (warp == 0) {
     // ================================ PRODUCER =========================================
@@ -233,6 +238,17 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
     const int pool_n = a.neg_pool_size_ptr ? __ldg(a.neg_pool_size_ptr) : a.neg_pool_size;
     float* b_isc = reinterpret_cast<float*>(b_act + 32);
     float* b_osc = b_isc + 32;
+    int64_t G0 = 0;                          // virtual positions emitted by earlier chunks
+    for (;;) {
+    long long c = 0;
+    if (lane == 0) c = (long long)atomicAdd(a.ctr, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= n_chunks) break;
+    const int64_t ra = c * (int64_t)a.chunk;
+    const int64_t rb = (ra + a.chunk < a.n_tokens) ? ra + a.chunk : a.n_tokens;
+    const int64_t len = rb - ra;
+    const int64_t nj = len + 2 * W;          // ring entries with a token behind them
+    const int64_t nv = len + 4 * W;          // virtual centres of this chunk
     for (int64_t i0 = 0; i0 < nv; i0 += 32) {
       {
         const int64_t i = i0 + lane;
@@ -292,16 +308,16 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
       __syncwarp();
       const int nb = (int)((nv - i0) < 32 ? (nv - i0) : 32);
       for (int l = 0; l < nb; ++l) {
-        const int64_t ii = i0 + l;
-        // ---- input-row ring -------------------------------------------------------------
-        if (ii < nj && lane == 0) {
+        const int64_t ii = G0 + i0 + l;                 // position in the CTA's virtual stream
+        // ---- input-row ring: every virtual position owns an entry (empty beyond the chunk) -----
+        if (lane == 0) {
           const int slot = (int)(ii % R);
           const uint32_t round = (uint32_t)(ii / R);
           mbar_wait(in_empty + slot, (round & 1u) ^ 1u);
           // a row nobody needed (shrunk window, break) can be released before its copy landed:
           // never re-arm a slot whose previous transaction is still in flight
           if (round > 0) mbar_wait(in_full + slot, (round - 1u) & 1u);
-          float* ptr = b_inptr[l];
+          float* ptr = (i0 + l < nj) ? b_inptr[l] : nullptr;
           in_ptr[slot] = ptr;
           in_scale[slot] = b_isc[l];
           if (ptr) {
@@ -326,7 +342,10 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
           out_meta[st].ptr[lane] = optr;
           out_meta[st].scale[lane] = b_osc[l * kKO + lane];
         }
-        if (lane == 0) out_meta[st].active = act;
+        if (lane == 0) {
+          out_meta[st].active = act;
+          out_meta[st].p = (long long)(ra - 2 * W + i0 + l);
+        }
         const uint32_t have = __ballot_sync(0xffffffffu, optr != nullptr);
         __syncwarp();     // every lane's meta pointer is written before the release-arrive
         if (lane == 0) {
@@ -339,6 +358,26 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
                    out_full + st);
       }
       __syncwarp();       // batch scratch is re-written next round
+    }
+    G0 += nv;
+    }
+    // out of work: one end marker per consumer warp (in stream order), then retire the counters
+    for (int k = 0; k < NW; ++k) {
+      const int64_t ii = G0 + k;
+      const int cw = (int)(ii % NW);
+      const int64_t n = ii / NW;
+      const int st = cw * 2 + (int)(n & 1);
+      if (lane == 0) {
+        mbar_wait(out_empty + st, (uint32_t)((n >> 1) & 1) ^ 1u);
+        out_meta[st].active = -1;
+        mbar_arrive(out_full + st);
+      }
+    }
+    if (lane == 0) {
+      if (atomicAdd(a.ctr + 1, 1u) == gridDim.x - 1) {   // every CTA has drawn its last ticket
+        a.ctr[0] = 0u;
+        a.ctr[1] = 0u;
+      }
     }
     return;
   }
@@ -356,7 +395,7 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
   for (int j = 0; j < VPL; ++j) lane_act[j] = (lane + 32 * j) < nvec;
 
   int64_t n = 0;
-  for (int64_t i = cw; i < nv; i += NW, ++n) {
+  for (int64_t i = cw;; i += NW, ++n) {
     const int st = cw * 2 + (int)(n & 1);
     mbar_wait(out_full + st, (uint32_t)((n >> 1) & 1));
     // the previous position's stage: its reductions were committed at the end of the last iteration;
@@ -366,8 +405,10 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
       mbar_arrive(out_empty + (st ^ 1));
     }
     const OutMeta* meta = out_meta + st;
-    if (meta->active) {
-      const int64_t p = ra - 2 * W + i;
+    const int active = meta->active;
+    if (active < 0) break;
+    if (active) {
+      const int64_t p = meta->p;
       unsigned char* rows = out_rows + (size_t)st * a.ko * a.row_bytes;
       float* my_ptr = (lane < KO) ? meta->ptr[lane] : nullptr;
       const float my_osc = (lane < KO) ? meta->scale[lane] : 1.f;
@@ -521,7 +562,7 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
     __syncwarp();
     if (lane <= 2 * W) {
       const int64_t j = i - 2 * W + lane;
-      if (j >= 0 && j < nj) mbar_arrive(in_empty + (int)(j % R));
+      if (j >= 0) mbar_arrive(in_empty + (int)(j % R));
     }
   }
   if (lane < kRelLanes) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // adds performed
@@ -587,11 +628,25 @@ extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream) {
     }
   }
   a.nw = nw;
+  void* ctr = nullptr;
+  MVB_CUDA_CHECK(cudaGetSymbolAddress(&ctr, g_win_ctr));
+  a.ctr = reinterpret_cast<unsigned int*>(ctr);
   int blocks = mvb_num_sms();
   if (h->max_ctas > 0 && h->max_ctas < blocks) blocks = h->max_ctas;
-  // every CTA gets a contiguous range; tiny inputs use fewer CTAs (>= 64 positions each)
+  // tiny inputs use fewer CTAs (>= 64 positions each)
   const int64_t by_len = (h->n_tokens + 63) / 64;
   if ((int64_t)blocks > by_len) blocks = (int)by_len;
+  // One chunk per CTA by default (a static partition: every chunk boundary drains and refills the rings, and
+  // the measured imbalance between CTAs is smaller than that: 1M tokens on 148 SMs, chunks of 256 / 512 /
+  // 1024 tokens ran at 103 / 106 / 107 M words/s against 110 with one chunk per CTA).  MVB_WIN_CHUNK=n hands
+  // out n-token chunks dynamically instead.
+  a.chunk = (int)((h->n_tokens + blocks - 1) / blocks);
+  if (const char* e = getenv("MVB_WIN_CHUNK")) {
+    const int v = atoi(e);
+    if (v >= 32 && v <= (1 << 20)) a.chunk = v;
+  }
+  const int64_t n_chunks = (h->n_tokens + a.chunk - 1) / a.chunk;
+  if ((int64_t)blocks > n_chunks) blocks = (int)n_chunks;
   const int vpl = (h->dim / 4 + 31) / 32;
   const size_t smem = (size_t)L.total;
 #define MVB_LAUNCH_WIN(V, K)                                                                         \

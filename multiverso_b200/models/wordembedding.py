@@ -245,7 +245,7 @@ class WordEmbedding:
 
     # ------------------------------------------------------------------ one data block
     def train_block(self, tokens: torch.Tensor, compute_loss: bool = True,
-                    next_tokens: Optional[torch.Tensor] = None) -> None:
+                    next_tokens: Optional[torch.Tensor] = None, next_ready: Optional[torch.cuda.Event] = None) -> None:
         """Train on one block of token ids (int32 CUDA tensor, negative = sentence break).
         Asynchronous on the current stream; read ``loss`` / ``pairs`` after a sync.
 
@@ -253,7 +253,9 @@ class WordEmbedding:
         RequestParameter run on a side stream while this block trains, and this block's
         AddDeltaParameter runs there while the next one trains -- the reference's pipeline
         (distributed_wordembedding.cpp:199-222: an extra thread prefetches the next block's
-        parameters during TrainIteration), with streams instead of an OpenMP thread."""
+        parameters during TrainIteration), with streams instead of an OpenMP thread.
+        ``next_ready``: event after which ``next_tokens`` is valid (e.g. recorded behind its H2D copy on a
+        copy stream); without it the block must be valid on the current stream at the time of the call."""
         assert tokens.is_cuda and tokens.dtype == torch.int32
         if self.rt.size == 1:
             with monitor("WE_TRAIN_BLOCK", cuda=True):
@@ -287,7 +289,7 @@ class WordEmbedding:
         trained.record(main)
         with torch.cuda.stream(side):
             if next_tokens is not None:
-                side.wait_event(inputs_ready)
+                side.wait_event(next_ready if next_ready is not None else inputs_ready)
                 nxt = self._prepare_block(next_tokens, wait=False)
                 nxt["tokens"] = next_tokens
                 nxt["ready"] = torch.cuda.Event()
