@@ -31,6 +31,8 @@ struct DenseAddDev {
   T* replica[MVB_MAX_RANKS];   // per-rank replica pointers (fallback without multicast)
   int has_replica;
   MvbAddOpt opts[MVB_MAX_RANKS];
+  MvbAddOpt* opt_box[MVB_MAX_RANKS];   // per rank: MVB_MAX_RANKS published AddOptions (or all nullptr)
+  int my_worker;
   float scale, clip;
   MvbPeers pads;
   int has_pads, me, world, ch_ready, ch_done, is_worker;
@@ -115,10 +117,21 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
   // A worker that called FinishTrain (Server_Finish_Train, src/server.cpp:190-213) leaves
   // MVB_EPOCH_FIN in its ready slot: it never blocks the others and contributes nothing.
   __shared__ unsigned int smask;
+  // The AddOption travels with the request (reference: last Blob of Request_Add): every worker publishes ITS
+  // option in each owner's option box before it signals `ready`; the owner applies worker w's delta with
+  // worker w's learning rate / momentum / rho / lambda.  Without boxes the by-value options are used.
+  __shared__ MvbAddOpt sopt[MVB_MAX_RANKS];
   if (threadIdx.x == 0) smask = a.mask;
+  if (threadIdx.x < MVB_MAX_RANKS) sopt[threadIdx.x] = a.opts[threadIdx.x];
   __syncthreads();
   if (a.has_pads) {
     if (blockIdx.x == 0 && a.is_worker && threadIdx.x < a.world) {
+      if (a.opt_box[threadIdx.x] != nullptr && a.my_worker >= 0) {
+        // two generations (epoch parity): an owner still finishing epoch e never sees epoch e+1's option,
+        // and epoch e+2 cannot be published before every owner has started epoch e+1
+        MvbAddOpt mine = a.opts[a.my_worker];
+        a.opt_box[threadIdx.x][(a.epoch & 1) * MVB_MAX_RANKS + a.my_worker] = mine;
+      }
       fence_sys();
       uint64_t* slot = reinterpret_cast<uint64_t*>(a.pads.p[threadIdx.x]) +
                        a.ch_ready * MVB_MAX_RANKS + a.me;
@@ -129,6 +142,15 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
                              a.ch_ready * MVB_MAX_RANKS + a.worker_rank[threadIdx.x];
       if (!spin_wait_ge(slot, a.epoch, a.budget)) { if (a.err) atomicExch(a.err, 3000 + threadIdx.x); }
       if (ld_acquire_sys_u64(slot) >= MVB_EPOCH_FIN) atomicAnd(&smask, ~(1u << threadIdx.x));
+      else if (a.opt_box[a.me] != nullptr) {
+        // published before that worker's ready flag (release) -> visible after the acquire above
+        const volatile int* src = reinterpret_cast<const volatile int*>(
+            a.opt_box[a.me] + (a.epoch & 1) * MVB_MAX_RANKS + threadIdx.x);
+        int* dst = reinterpret_cast<int*>(&sopt[threadIdx.x]);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(MvbAddOpt) / 4); ++k) dst[k] = src[k];
+        sopt[threadIdx.x].worker_id = threadIdx.x;
+      }
     }
     __syncthreads();
   }
@@ -146,10 +168,10 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
         float4 sum = multimem_ld_reduce_add_v4_f32(a.delta_mc + a.shard_off + i);
         Pack<T, VEC> d = pk_load<T, VEC>(a.shard + i);
         T z0 = 0, z1 = 0;
-        U::Apply(d.v[0], prep_delta<T>(sum.x, a.scale, a.clip), z0, z1, a.opts[0]);
-        U::Apply(d.v[1], prep_delta<T>(sum.y, a.scale, a.clip), z0, z1, a.opts[0]);
-        U::Apply(d.v[2], prep_delta<T>(sum.z, a.scale, a.clip), z0, z1, a.opts[0]);
-        U::Apply(d.v[3], prep_delta<T>(sum.w, a.scale, a.clip), z0, z1, a.opts[0]);
+        U::Apply(d.v[0], prep_delta<T>(sum.x, a.scale, a.clip), z0, z1, sopt[0]);
+        U::Apply(d.v[1], prep_delta<T>(sum.y, a.scale, a.clip), z0, z1, sopt[0]);
+        U::Apply(d.v[2], prep_delta<T>(sum.z, a.scale, a.clip), z0, z1, sopt[0]);
+        U::Apply(d.v[3], prep_delta<T>(sum.w, a.scale, a.clip), z0, z1, sopt[0]);
         pk_store<T, VEC>(a.shard + i, d);
         if (a.has_replica) push_replica<T, VEC>(a, i, d);
         continue;
@@ -175,7 +197,7 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
-          U::Apply(d.v[e], prep_delta<T>(g[w].v[e], a.scale, a.clip), s0.v[e], s1.v[e], a.opts[w]);
+          U::Apply(d.v[e], prep_delta<T>(g[w].v[e], a.scale, a.clip), s0.v[e], s1.v[e], sopt[w]);
         if constexpr (U::kPerWorker) {
           pk_store<T, VEC>(a.state0 + (int64_t)w * a.state_stride + i, s0);
           if constexpr (U::kStates >= 2)
@@ -200,7 +222,7 @@ add_dense_fused_kernel(const __grid_constant__ DenseAddDev<T> a) {
           if constexpr (U::kStates >= 2) s1 = a.state1[(int64_t)w * a.state_stride + i];
         }
         U::Apply(d, prep_delta<T>(__ldg(a.delta[w] + a.shard_off + i), a.scale, a.clip), s0, s1,
-                 a.opts[w]);
+                 sopt[w]);
         if constexpr (U::kPerWorker) {
           a.state0[(int64_t)w * a.state_stride + i] = s0;
           if constexpr (U::kStates >= 2) a.state1[(int64_t)w * a.state_stride + i] = s1;
@@ -254,9 +276,11 @@ int launch_add(const MvbDenseAdd* h, cudaStream_t st) {
   for (int w = 0; w < MVB_MAX_RANKS; ++w) {
     a.delta[w] = w < h->nworkers ? (const T*)h->delta_ptrs[w] : nullptr;
     a.opts[w] = h->opts[w];
+    a.opt_box[w] = reinterpret_cast<MvbAddOpt*>(h->opt_box[w]);
     a.worker_rank[w] = h->worker_rank[w];
     if (w < h->nworkers && !aligned16<T>(h->delta_ptrs[w])) vec_ok = false;
   }
+  a.my_worker = h->my_worker;
   a.delta_mc = (const T*)h->delta_multicast;
   a.has_replica = h->replica_ptrs[0] != nullptr || h->replica_multicast != nullptr;
   a.replica_mc = (T*)h->replica_multicast;

@@ -199,6 +199,104 @@ __global__ void regularize_kernel(float* grad, const float* w, int64_t len, int 
   }
 }
 
+// ---- wide dense models (> 64 classes / GEMM-sized minibatches): the two products run on the tcgen05
+// kernel of gemm_fused.cu (logits = X W^T with W streamed from its table, grad = E^T X); this is the
+// epilogue between them: per sample softmax / sigmoid / linear, loss, accuracy and the error matrix
+// E = (P - Y) * sample_weight / n, written TRANSPOSED ([out x n_pad], zero padded) so that it is the
+// K-major left operand of the gradient GEMM.  One warp per sample, any number of classes.
+__global__ void __launch_bounds__(128)
+lr_wide_epilogue_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int64_t n, int out,
+                        int objective, float inv_n, float* __restrict__ err_t, int64_t n_pad,
+                        float* __restrict__ pred, float* __restrict__ loss_sum, int* __restrict__ correct) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float loss_acc = 0.f;
+  int corr_acc = 0;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const float* z = logits + i * out;
+    const float y = labels[i];
+    if (out == 1) {
+      if (lane == 0) {
+        float p = z[0], l;
+        if (objective >= 1) {
+          p = 1.f / (1.f + __expf(-p));
+          l = -(y * __logf(fmaxf(p, 1e-30f)) + (1.f - y) * __logf(fmaxf(1.f - p, 1e-30f)));
+          corr_acc += ((p > 0.5f) == (y > 0.5f));
+        } else {
+          l = 0.5f * (p - y) * (p - y);
+          corr_acc += (fabsf(p - y) < 0.5f);
+        }
+        loss_acc += l;
+        err_t[i] = (p - y) * inv_n;
+        if (pred) pred[i] = p;
+      }
+      continue;
+    }
+    const int label = (int)y;
+    float mx = -3.4e38f;
+    int arg = 0;
+    for (int c = lane; c < out; c += 32) { const float v = z[c]; if (v > mx) { mx = v; arg = c; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    float denom = 0.f;
+    if (objective == 2) {
+      for (int c = lane; c < out; c += 32) denom += __expf(z[c] - mx);
+      denom = warp_sum(denom);
+    }
+    float l = 0.f;
+    for (int c = lane; c < out; c += 32) {
+      const float t = (c == label) ? 1.f : 0.f;
+      float p;
+      if (objective == 2) {
+        p = __expf(z[c] - mx) / denom;
+        if (c == label) l -= __logf(fmaxf(p, 1e-30f));
+      } else if (objective == 1) {
+        p = 1.f / (1.f + __expf(-z[c]));
+        l -= t * __logf(fmaxf(p, 1e-30f)) + (1.f - t) * __logf(fmaxf(1.f - p, 1e-30f));
+      } else {
+        p = z[c];
+        l += 0.5f * (p - t) * (p - t);
+      }
+      err_t[(int64_t)c * n_pad + i] = (p - t) * inv_n;
+      if (pred) pred[i * out + c] = p;
+    }
+    l = warp_sum(l);
+    if (lane == 0) { loss_acc += l; corr_acc += (arg == label); }
+  }
+  if (lane == 0) {
+    if (loss_sum && loss_acc != 0.f) atomicAdd(loss_sum, loss_acc);
+    if (correct && corr_acc) atomicAdd(correct, corr_acc);
+  }
+}
+
+// out[c][r] = in[r][c] (in: [rows x cols] with pitch ld_in; out: [cols x ld_out], columns >= rows zeroed)
+__global__ void __launch_bounds__(256)
+transpose_pad_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
+                     float* __restrict__ out, int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t c = c0 + k, r = r0 + tx;
+    if (c < cols && r < ld_out) out[c * ld_out + r] = tile[tx][k];
+  }
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n, float alpha) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] += alpha * x[i];
+}
+
 int ew_blocks(int64_t n) {
   int64_t b = (n + 255) / 256;
   int64_t cap = (int64_t)mvb_num_sms() * 8;
@@ -247,6 +345,38 @@ extern "C" int mvb_ftrl_update(float* z, float* n, const float* w, const float* 
 extern "C" int mvb_regularize(float* grad, const float* w, int64_t len, int type, float coef,
                               void* stream) {
   regularize_kernel<<<ew_blocks(len), 256, 0, (cudaStream_t)stream>>>(grad, w, len, type, coef);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Epilogue of the wide dense path (see lr_wide_epilogue_kernel): err_t is [out x n_pad], n_pad % 4 == 0.
+extern "C" int mvb_lr_wide_epilogue(const float* logits, const float* labels, int64_t n, int out, int objective,
+                                    float* err_t, int64_t n_pad, float* pred, float* loss_sum, int* correct,
+                                    void* stream) {
+  if (n <= 0) return 0;
+  if (out < 1 || n_pad < n) return -8;
+  cudaStream_t st = (cudaStream_t)stream;
+  MVB_CUDA_CHECK(cudaMemsetAsync(err_t, 0, (size_t)out * n_pad * sizeof(float), st));
+  int64_t blocks = (n + 3) / 4;
+  const int64_t cap = (int64_t)mvb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  lr_wide_epilogue_kernel<<<(int)blocks, 128, 0, st>>>(logits, labels, n, out, objective, 1.0f / (float)n, err_t,
+                                                       n_pad, pred, loss_sum, correct);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+// out[c][r] = in[r][c]; out pitch ld_out >= rows, the pad columns are written as zeros.
+extern "C" int mvb_transpose_pad_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                                     int64_t ld_out, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((ld_out + 31) / 32));
+  transpose_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, rows, cols, ld_in, out, ld_out);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mvb_axpy_f32(float* y, const float* x, int64_t n, float alpha, void* stream) {
+  if (n <= 0) return 0;
+  axpy_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(y, x, n, alpha);
   MVB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -117,6 +117,12 @@ typedef struct MvbDenseAdd {
   int* fin_flag;          /* device int, set to 1 when every worker has finished */
   unsigned int* done_counter; /* device uint, zero-initialised         */
   double timeout_s;
+  /* per-worker AddOptions through symmetric memory (optional): opt_box[r] = rank r's option box
+     (2 x MVB_MAX_RANKS MvbAddOpt, peer mapped).  The calling worker publishes opts[my_worker] in every
+     owner's box before its ready flag; owners apply worker w's delta with worker w's published option.
+     NULL boxes: opts[] are used as given (single process / identical options).                       */
+  void* opt_box[MVB_MAX_RANKS];
+  int my_worker;          /* this rank's worker id (-1: not a worker)  */
 } MvbDenseAdd;
 int mvb_add_dense_fused(const MvbDenseAdd* a, void* stream);
 
@@ -370,6 +376,14 @@ typedef struct MvbLrDense {
   int compute_grad;
 } MvbLrDense;
 int mvb_lr_dense_fwd_bwd(const MvbLrDense* a, void* stream);
+/* wide dense path (> 64 classes / GEMM-sized minibatches): logits and gradient run on the tcgen05 kernel
+   (mvb_get_gemm_fused); this is the softmax / sigmoid / linear epilogue between the two products: loss,
+   accuracy, predictions and the error matrix E^T = ((P - Y) / n)^T as [out x n_pad] (zero padded).     */
+int mvb_lr_wide_epilogue(const float* logits, const float* labels, int64_t n, int out, int objective,
+                         float* err_t, int64_t n_pad, float* pred, float* loss_sum, int* correct, void* stream);
+int mvb_transpose_pad_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                          int64_t ld_out, void* stream);
+int mvb_axpy_f32(float* y, const float* x, int64_t n, float alpha, void* stream);
 /* FTRL-proximal: weights from (z,n); gradient emits (dz,dn) (reference objective.cpp:260-336) */
 int mvb_ftrl_weights(const float* z, const float* n, float* w, int64_t len, float alpha, float beta,
                      float l1, float l2, void* stream);

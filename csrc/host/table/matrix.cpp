@@ -1,5 +1,6 @@
 // Matrix<T> with sparse delta-pull and optional wire compression
 // (see include/multiverso/table/matrix.h and table/sparse_matrix_table.h).
+#include <algorithm>
 #include "multiverso/table/matrix.h"
 #include "multiverso/multiverso.h"
 #include "multiverso/table/sparse_matrix_table.h"
@@ -35,11 +36,18 @@ int MatrixWorker<T>::SubmitWholeAdd(T* data, size_t size, const AddOption* opt) 
     for (integer_t c = 0; c < C && !nz; ++c) nz = row[c] != T(0);
     if (nz) rows.push_back(r);
   }
-  if (rows.empty()) {
-    // nothing to ship: an already-complete request (the reference sends a dummy zero row)
-    const int id = this->NewRequest();
-    this->Reset(id, 0);
-    return id;
+  {
+    // Every server must SEE this whole-table Add, also the ones none of the non-zero rows belongs to: under
+    // -sync the SyncServer counts one Add per worker per step (src/server.cpp:141-163), and a worker that
+    // skips a server would leave the other workers' Gets parked there until FinishTrain.  Like the
+    // reference's dummy zero row (src/table/matrix.cpp:166-170), servers without a non-zero row get one
+    // all-zero placeholder row (their first row: it IS all zero in `data`, adding it changes nothing).
+    std::vector<char> seen(static_cast<size_t>(this->part_.num_servers), 0);
+    for (integer_t r : rows) seen[static_cast<size_t>(this->part_.ServerOf(r))] = 1;
+    bool added = false;
+    for (int s = 0; s < this->part_.num_servers; ++s)
+      if (!seen[static_cast<size_t>(s)]) { rows.push_back(this->part_.row_begin[s]); added = true; }
+    if (added) std::sort(rows.begin(), rows.end());
   }
   Blob vals(rows.size() * C * sizeof(T));
   ParallelFor(static_cast<int64_t>(rows.size()), rows.size() >= 2048 ? std::max(1, MV_CONFIG(omp_threads)) : 1,

@@ -52,7 +52,7 @@ class DenseAdd(C.Structure):
         ("clip", C.c_float), ("pads", C.POINTER(vp)), ("me", C.c_int), ("world", C.c_int),
         ("ch_ready", C.c_int), ("ch_done", C.c_int), ("epoch", C.c_uint64), ("worker_rank", I32x8),
         ("is_worker", C.c_int), ("err_flag", vp), ("fin_flag", vp), ("done_counter", vp),
-        ("timeout_s", C.c_double),
+        ("timeout_s", C.c_double), ("opt_box", VP8), ("my_worker", C.c_int),
     ]
 
 

@@ -16,6 +16,7 @@ regular/regular.cpp, updater/updater.cpp) -- with the hot loops on the GPU:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -132,6 +133,22 @@ def dense_gemm_step(x: torch.Tensor, labels: torch.Tensor, w: torch.Tensor, grad
     return loss, correct, p
 
 
+def _tc_gemm_nt(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[M, N] = x[M, K] @ w[N, K]^T on the hand-written tcgen05 kernel (gemm_fused.cu: TMA-fed
+    tcgen05.mma, CTA pairs, TF32 operands, fp32 accumulation in TMEM) -- `w` is presented as a one-server
+    row map, so the same kernel that streams table shards multiplies two local matrices.  K % 4 == 0."""
+    M, K = x.shape
+    Nr = w.shape[0]
+    g = N.GetGemm()
+    g.x, g.y, g.w_cache = x.data_ptr(), out.data_ptr(), None
+    g.M, g.N, g.K = M, Nr, K
+    g.wmap.num_row, g.wmap.num_col, g.wmap.nservers, g.wmap.rows_per_server = Nr, K, 1, Nr
+    g.wmap.shard_ptrs[0] = w.data_ptr()
+    g.local_server = 0
+    N.check(N.cuda_lib().mvb_get_gemm_fused(C.byref(g), C.c_void_p(N.stream_ptr())), "mvb_get_gemm_fused")
+    return out
+
+
 class LogRegModel:
     """Model (local) / PSModel (``use_ps``) on the device backend."""
 
@@ -223,7 +240,35 @@ class LogRegModel:
 
     def forward_backward_dense(self, x, labels, train=True, pred=None):
         n = labels.numel()
-        if self.out >= GEMM_PATH_MIN_CLASSES or n * self.dim * self.out >= GEMM_PATH_MIN_WORK:
+        wide = self.out >= GEMM_PATH_MIN_CLASSES or n * self.dim * self.out >= GEMM_PATH_MIN_WORK
+        if wide and self.dim % 4 == 0 and x.is_cuda and os.environ.get("MVB_LR_TC", "1") != "0":
+            # GEMM-shaped minibatch: logits = X W^T and grad += E^T X both on the tcgen05 kernel (TF32 in,
+            # fp32 accumulate), softmax / loss / error in the hand-written epilogue between them; no
+            # library GEMM anywhere (Objective::Predict + Gradient, objective.cpp:113-120, 202-218)
+            lib, st = N.cuda_lib(), C.c_void_p(N.stream_ptr())
+            dev = x.device
+            x2 = x.view(n, self.dim)
+            n_pad = (n + 3) // 4 * 4
+            logits = torch.empty(n, self.out, device=dev)
+            _tc_gemm_nt(x2, self._weights().view(self.out, self.dim), logits)
+            err_t = torch.empty(self.out, n_pad, device=dev)
+            N.check(lib.mvb_lr_wide_epilogue(C.c_void_p(logits.data_ptr()), C.c_void_p(labels.data_ptr()), C.c_int64(n),
+                                             C.c_int(self.out), C.c_int(self.objective), C.c_void_p(err_t.data_ptr()),
+                                             C.c_int64(n_pad), C.c_void_p(N.ptr(pred)), C.c_void_p(self.loss.data_ptr()),
+                                             C.c_void_p(self.correct.data_ptr()), st), "mvb_lr_wide_epilogue")
+            self.kernel_launches += 2
+            if train:
+                x_t = torch.empty(self.dim, n_pad, device=dev)
+                N.check(lib.mvb_transpose_pad_f32(C.c_void_p(x2.data_ptr()), C.c_int64(n), C.c_int64(self.dim),
+                                                  C.c_int64(self.dim), C.c_void_p(x_t.data_ptr()), C.c_int64(n_pad), st),
+                        "mvb_transpose_pad_f32")
+                dw = torch.empty(self.out, self.dim, device=dev)
+                _tc_gemm_nt(err_t, x_t, dw)                      # [out x n] . [dim x n]^T
+                N.check(lib.mvb_axpy_f32(C.c_void_p(self.grad.data_ptr()), C.c_void_p(dw.data_ptr()),
+                                         C.c_int64(self.out * self.dim), C.c_float(1.0), st), "mvb_axpy_f32")
+                self.kernel_launches += 3
+            return
+        if wide:
             loss, correct, p = dense_gemm_step(x.view(n, self.dim), labels, self._weights(),
                                                self.grad if train else None, self.objective, self.out)
             self.loss += loss

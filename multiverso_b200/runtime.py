@@ -91,15 +91,27 @@ class SymmBuffer:
             arr[r] = self.ptrs[r] if r < len(self.ptrs) else None
         return arr
 
-    def free(self):
+    def close_peers(self):
+        """Phase 1 of a release: unmap the peers' slabs from this process."""
         lib = N.cuda_lib()
         for q in self._opened:
             lib.mvb_ipc_close_handle(C.c_void_p(q))
         self._opened = []
+
+    def free_local(self):
+        """Phase 2: free the exported slab -- only after EVERY rank has finished phase 1 (a peer that still
+        has the slab mapped must never see it freed; same ordering as csrc/device_rt/device_rt.cpp)."""
         if self.local_ptr:
             self._base = None
-            lib.mvb_symm_free(C.c_void_p(self.local_ptr))
+            N.cuda_lib().mvb_symm_free(C.c_void_p(self.local_ptr))
             self.local_ptr = 0
+
+    def free(self):
+        """Collective release: close peer mappings, rendezvous, free the local slab."""
+        self.close_peers()
+        if self.rt.size > 1 and self.rt.started:
+            self.rt.control_barrier()
+        self.free_local()
 
 
 class McBuffer:
@@ -247,17 +259,26 @@ class Runtime:
         self._finish_train()
         self.barrier()
         for t in list(self.tables):
-            if hasattr(t, "free"):
+            if self.backend != "device" and hasattr(t, "free"):
                 t.free()
-        self.tables = []
+        self.tables = []          # device tables: every symmetric slab is released below, in two phases
         if self.backend == "device":
             torch.cuda.synchronize()
-            for b in self._symm:
-                b.free()
+            # two-phase release of every symmetric allocation: all ranks unmap their peers' slabs, meet on
+            # the control plane, and only then free the slabs they exported
+            bufs = list(self._symm) + ([self.pads] if self.pads is not None else [])
+            for b in bufs:
+                if hasattr(b, "close_peers"):
+                    b.close_peers()
+            if self.size > 1:
+                self.control_barrier()
+            for b in bufs:
+                if hasattr(b, "free_local"):
+                    b.free_local()
+                else:
+                    b.free()
             self._symm = []
-            if self.pads is not None:
-                self.pads.free()
-                self.pads = None
+            self.pads = None
         if finalize_net and self._own_pg:
             import torch.distributed as dist
             if dist.is_initialized():
@@ -327,6 +348,11 @@ class Runtime:
         return self.rank in self.server_ranks
 
     # ------------------------------------------------------------------ control plane
+    def control_barrier(self) -> None:
+        """Host-side rendezvous on the control plane (no device work involved)."""
+        if self.size > 1:
+            self.all_gather_object(0)
+
     def all_gather_object(self, obj):
         if self.size == 1:
             return [obj]

@@ -141,6 +141,11 @@ class DenseDeviceTable(_AsyncOps):
         self._finished = False
         self._replica = None          # fused Add -> Get: full-table replica on every rank
         self._replica_epoch = -1
+        self._opt_box = None
+        if rt.size > 1 and self.sync:
+            # option boxes of the collective Add (the worker's AddOption travels with its request)
+            self._opt_box = rt.alloc_symm(2 * N.MAX_RANKS * 32)
+            self._opt_box.tensor(torch.uint8).zero_()
         self.table_id = rt.register_table(self)
         rt.barrier()   # MV_CreateTable ends with a barrier (multiverso.h:35-41)
 
@@ -207,10 +212,10 @@ class DenseDeviceTable(_AsyncOps):
                         buf.tensor(self.dtype, self.size).copy_(self._as_device(delta))
                 else:
                     buf = self._cur_stage
+                # The option travels with the request (reference: last Blob of Request_Add): this worker's
+                # AddOption is published through the symmetric option boxes inside the fused kernel, right
+                # before its ready flag; every owner applies worker w's delta with worker w's option.
                 opts = [opt] * self.W
-                # per-worker options travel with the request in the reference; here every
-                # worker's option is its own -- gather the 20-byte structs once per call only
-                # when a stateful updater needs per-worker learning rates.
                 ptrs = [buf.ptrs[rt.worker_id_to_rank(w)] for w in range(self.W)]
                 # NVLS: when the staging is multicast-bound and every rank is a worker the owner
                 # reduces its slice inside the switch instead of pulling W copies
@@ -240,6 +245,18 @@ class DenseDeviceTable(_AsyncOps):
                 self._keep = src
         return self._record()
 
+    def _opt_box_buf(self):
+        """Symmetric option boxes (2 generations x MAX_RANKS AddOptions per rank); allocated at the first
+        collective Add, which every rank reaches together."""
+        b = self._opt_box
+        if b is None:                       # async table used collectively (e.g. an explicit staged Add)
+            b = self.rt.alloc_symm(2 * N.MAX_RANKS * 32)
+            b.tensor(torch.uint8).zero_()
+            torch.cuda.synchronize()
+            self.rt.barrier()
+            self._opt_box = b
+        return b
+
     def _launch_fused(self, delta_ptrs: Sequence[int], opts: Sequence[AddOption], pads: bool,
                       serve_only: bool = False, multicast: int = 0) -> None:
         rt, lib = self.rt, N.cuda_lib()
@@ -258,6 +275,11 @@ class DenseDeviceTable(_AsyncOps):
             a.opts[w].worker_id = w
             a.worker_rank[w] = rt.worker_id_to_rank(w) if rt.size > 1 else 0
         a.scale, a.clip = 1.0, 0.0
+        a.my_worker = rt.worker_id() if rt.size > 1 else 0
+        if pads and rt.size > 1:
+            box = self._opt_box_buf()
+            for r in range(rt.size):
+                a.opt_box[r] = box.ptrs[r]
         a.delta_multicast = multicast or None
         if pads and self._replica is not None:
             for r in range(rt.size):

@@ -48,6 +48,16 @@ def scenario_sync():
         s = 0.5 * s + 0.5 * (w + 1)
         x -= s
     check("bsp_momentum_sequential", torch.allclose(tm.get(), torch.full((10007,), x, device="cuda")))
+    # the AddOption travels with each worker's request: per-worker learning rates under AdaGrad (per-worker
+    # history): worker w adds delta = lr_w twice -> owner moves by rho/sqrt(1) + rho/sqrt(2) for EVERY worker
+    # only if it divides by the pushing worker's own learning rate
+    to = mv.ArrayTable(70001, "float32", updater="adagrad")
+    lr_w = 0.01 * (r + 1)
+    for it in range(2):
+        to.add(torch.full((70001,), lr_w, device="cuda"), mv.AddOption(learning_rate=lr_w, rho=0.1))
+    exp_o = -W * (0.1 / 1.0 + 0.1 / (2 ** 0.5))
+    check("bsp_per_worker_addoption", torch.allclose(to.get(), torch.full((70001,), exp_o, device="cuda"), rtol=1e-4),
+          f"{to.get()[:2].tolist()} vs {exp_o}")
     # matrix scenario (test_matrix_table.cpp): whole + rows 0,1,3,7
     rows, cols = 1000, 64
     m = mv.MatrixTable(rows, cols, "float32")

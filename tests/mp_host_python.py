@@ -22,6 +22,20 @@ for count in range(1, 4):
     exp = base * count * W
     exp[[0, 1, 5, 10]] *= 2
     assert np.array_equal(m.get(), exp)
+# sparse (delta-pull) table under BSP: a worker whose whole-table delta is all zero must still be SEEN by
+# every server (one Add per worker per step) -- otherwise the others' Gets stay parked until FinishTrain
+sp = mv.MatrixTable(12, 4, "float32", is_sparse=True)
+for it in range(1, 4):
+    delta = np.zeros((12, 4), np.float32)
+    if mv.rank() != 1:                       # rank 1 contributes nothing at all
+        delta[mv.rank() % 12] = 1.0
+    sp.add(delta)
+    got = sp.get()
+    exp_sp = np.zeros((12, 4), np.float32)
+    for r in range(W):
+        if r != 1:
+            exp_sp[r % 12] += it
+    assert np.array_equal(np.asarray(got).reshape(12, 4), exp_sp), (it, got)
 kv = mv.KVTable("int64", "float32")
 kv.add([1, 2, 1000003], [1.0, 2.0, 0.5])
 mv.barrier()
