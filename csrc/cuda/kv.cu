@@ -118,6 +118,33 @@ __global__ void kv_dump_kernel(const long long* keys, const V* vals, int64_t cap
   }
 }
 
+// growth: number of live keys of a shard, and re-insertion of a shard into a larger local table
+__global__ void kv_count_kernel(const long long* keys, int64_t cap, unsigned long long* count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) c += keys[i] != kEmpty;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+template <typename V>
+__global__ void kv_rehash_kernel(const long long* okeys, const V* ovals, int64_t ocap, long long* nkeys, V* nvals,
+                                 int64_t ncap, int* err) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += stride) {
+    const long long key = okeys[i];
+    if (key == kEmpty) continue;
+    uint64_t slot = mix64((uint64_t)key) & (uint64_t)(ncap - 1);
+    bool done = false;
+    for (int64_t probe = 0; probe < ncap; ++probe) {
+      const long long cur = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(nkeys + slot),
+                                                 (unsigned long long)kEmpty, (unsigned long long)key);
+      if (cur == kEmpty) { nvals[slot] = ovals[i]; done = true; break; }   // keys are unique in the old table
+      slot = (slot + 1) & (uint64_t)(ncap - 1);
+    }
+    if (!done && err) atomicExch(err, 5002);
+  }
+}
+
 KVDev to_dev(const MvbKV* h) {
   KVDev d{};
   d.S = h->nservers;
@@ -186,6 +213,31 @@ extern "C" int mvb_kv_dump(int vtype, const void* keys, const void* vals, int64_
     case MVB_F64: kv_dump_kernel<double><<<b, 256, 0, st>>>((const long long*)keys, (const double*)vals, capacity, (long long*)out_keys, (double*)out_vals, (unsigned long long*)out_count); break;
     case MVB_I32: kv_dump_kernel<int><<<b, 256, 0, st>>>((const long long*)keys, (const int*)vals, capacity, (long long*)out_keys, (int*)out_vals, (unsigned long long*)out_count); break;
     case MVB_I64: kv_dump_kernel<long long><<<b, 256, 0, st>>>((const long long*)keys, (const long long*)vals, capacity, (long long*)out_keys, (long long*)out_vals, (unsigned long long*)out_count); break;
+    default: return -1;
+  }
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Live keys of one shard (device count, zeroed here).
+extern "C" int mvb_kv_count(const void* keys, int64_t capacity, int64_t* out_count, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MVB_CUDA_CHECK(cudaMemsetAsync(out_count, 0, 8, st));
+  kv_count_kernel<<<blocks_for(capacity), 256, 0, st>>>((const long long*)keys, capacity, (unsigned long long*)out_count);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+// Re-insert every live (key, value) of a shard into a new, initialised, larger LOCAL table (growth).
+extern "C" int mvb_kv_rehash(int vtype, const void* old_keys, const void* old_vals, int64_t old_cap, void* new_keys,
+                             void* new_vals, int64_t new_cap, int* err_flag, void* stream) {
+  if (new_cap & (new_cap - 1)) return -4;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int b = blocks_for(old_cap);
+  switch (vtype) {
+    case MVB_F32: kv_rehash_kernel<float><<<b, 256, 0, st>>>((const long long*)old_keys, (const float*)old_vals, old_cap, (long long*)new_keys, (float*)new_vals, new_cap, err_flag); break;
+    case MVB_F64: kv_rehash_kernel<double><<<b, 256, 0, st>>>((const long long*)old_keys, (const double*)old_vals, old_cap, (long long*)new_keys, (double*)new_vals, new_cap, err_flag); break;
+    case MVB_I32: kv_rehash_kernel<int><<<b, 256, 0, st>>>((const long long*)old_keys, (const int*)old_vals, old_cap, (long long*)new_keys, (int*)new_vals, new_cap, err_flag); break;
+    case MVB_I64: kv_rehash_kernel<long long><<<b, 256, 0, st>>>((const long long*)old_keys, (const long long*)old_vals, old_cap, (long long*)new_keys, (long long*)new_vals, new_cap, err_flag); break;
     default: return -1;
   }
   MVB_CUDA_CHECK(cudaGetLastError());

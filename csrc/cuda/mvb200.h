@@ -203,6 +203,10 @@ typedef struct MvbKV {
   void* vals[MVB_MAX_RANKS];
 } MvbKV;
 int mvb_kv_init(void* keys, int64_t capacity, void* stream);
+/* growth: live keys of a shard; re-insertion of a shard into a larger (initialised) local table */
+int mvb_kv_count(const void* keys, int64_t capacity, int64_t* out_count, void* stream);
+int mvb_kv_rehash(int vtype, const void* old_keys, const void* old_vals, int64_t old_cap, void* new_keys,
+                  void* new_vals, int64_t new_cap, int* err_flag, void* stream);
 int mvb_kv_add(const MvbKV* kv, const int64_t* keys, const void* vals, int64_t n, int* err_flag,
                void* stream);
 int mvb_kv_get(const MvbKV* kv, const int64_t* keys, void* out_vals, int64_t n, void* stream);
@@ -282,6 +286,13 @@ int mvb_sgns_train(const MvbSgns* a, void* stream);
 int mvb_sgns_train_tma(const MvbSgns* a, void* stream);   /* TMA bulk-copy pipeline variant */
 int mvb_sgns_train_win(const MvbSgns* a, void* stream);   /* window-batched TMA pipeline      */
 int mvb_sgns_win_inflight(int dim, int negative, int window, int max_ctas);  /* centre positions in flight */
+/* ---- staleness instrumentation: per-shard version counters (symmetric memory), bumped by every Add,
+   recorded by every Get; staleness of an Add = other workers' Adds applied since this worker's last Get */
+int mvb_stale_on_add(void* const* version_ptrs, int nservers, unsigned long long* last_get,
+                     unsigned int* adds_since, unsigned long long* hist, int nbins, void* stream);
+int mvb_stale_on_get(void* const* version_ptrs, int nservers, unsigned long long* last_get,
+                     unsigned int* adds_since, void* stream);
+
 /* ---- row mailboxes (rowbox.cu): device-side row Add with owner-side apply ------------- */
 typedef struct MvbRowBox {
   MvbRowMap map;             /* the table's shards (fp32, num_col % 4 == 0, every rank worker + server)   */

@@ -226,3 +226,47 @@ extern "C" int mvb_barrier(void* const* pads, int me, int world, int channel, ui
   MVB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Staleness instrumentation (BASELINE config 5).  Every shard carries a version counter
+// in its owner's symmetric memory.  A worker's Add bumps the counter of every shard it updates and learns,
+// from the value it replaced, how many OTHER workers' Adds were applied to that shard since this worker
+// last pulled it -- the staleness of the gradient it has just pushed, the quantity the DC-ASGD updaters
+// compensate (include/multiverso/updater/dcasgd).  A Get records the versions it saw.  All bookkeeping
+// stays on the device (one warp, a few system-scope atomics per op); the histogram is read at display time.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void stale_on_add_kernel(MvbPeers ver, int S, unsigned long long* last_get, unsigned int* adds_since,
+                                    unsigned long long* hist, int nbins) {
+  const int s = threadIdx.x;
+  if (s >= S || ver.p[s] == nullptr) return;
+  const unsigned long long old = atomicAdd_system(reinterpret_cast<unsigned long long*>(ver.p[s]), 1ull);
+  long long st = (long long)old - (long long)last_get[s] - (long long)adds_since[s];
+  if (st < 0) st = 0;
+  adds_since[s] += 1u;
+  atomicAdd(hist + (st < nbins - 1 ? st : nbins - 1), 1ull);
+}
+__global__ void stale_on_get_kernel(MvbPeers ver, int S, unsigned long long* last_get, unsigned int* adds_since) {
+  const int s = threadIdx.x;
+  if (s >= S || ver.p[s] == nullptr) return;
+  last_get[s] = ld_relaxed_sys_u64(reinterpret_cast<const uint64_t*>(ver.p[s]));
+  adds_since[s] = 0u;
+}
+}  // namespace
+
+extern "C" int mvb_stale_on_add(void* const* version_ptrs, int nservers, unsigned long long* last_get,
+                                unsigned int* adds_since, unsigned long long* hist, int nbins, void* stream) {
+  MvbPeers v{};
+  for (int s = 0; s < MVB_MAX_RANKS; ++s) v.p[s] = s < nservers ? version_ptrs[s] : nullptr;
+  stale_on_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(v, nservers, last_get, adds_since, hist, nbins);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mvb_stale_on_get(void* const* version_ptrs, int nservers, unsigned long long* last_get,
+                                unsigned int* adds_since, void* stream) {
+  MvbPeers v{};
+  for (int s = 0; s < MVB_MAX_RANKS; ++s) v.p[s] = s < nservers ? version_ptrs[s] : nullptr;
+  stale_on_get_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(v, nservers, last_get, adds_since);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

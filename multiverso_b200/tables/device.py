@@ -141,6 +141,16 @@ class DenseDeviceTable(_AsyncOps):
         self._finished = False
         self._replica = None          # fused Add -> Get: full-table replica on every rank
         self._replica_epoch = -1
+        # staleness instrumentation (-staleness=true): one version counter per shard in its owner's memory
+        self._ver = None
+        if bool(FLAGS.get("staleness")):
+            self._ver = rt.alloc_symm(64)
+            self._ver.tensor(torch.int64).zero_()
+            self._ver_ptrs = (C.c_void_p * N.MAX_RANKS)(*[self._ver.ptrs[rt.server_id_to_rank(s)] if s < S else None
+                                                          for s in range(N.MAX_RANKS)])
+            self._ver_last = torch.zeros(N.MAX_RANKS, dtype=torch.int64, device=rt.device)
+            self._ver_adds = torch.zeros(N.MAX_RANKS, dtype=torch.int32, device=rt.device)
+            self.staleness_hist = torch.zeros(64, dtype=torch.int64, device=rt.device)
         self._opt_box = None
         if rt.size > 1 and self.sync:
             # option boxes of the collective Add (the worker's AddOption travels with its request)
@@ -243,7 +253,22 @@ class DenseDeviceTable(_AsyncOps):
                                                         self.S, sp, s0, s1, so, sl, ss, C.byref(ao), rt.rank,
                                                         C.c_void_p(N.stream_ptr())), "mvb_push_dense_stateful")
                 self._keep = src
+            if rt.is_worker():
+                self._note_add()
         return self._record()
+
+    def _note_add(self) -> None:
+        if self._ver is not None:
+            N.check(N.cuda_lib().mvb_stale_on_add(self._ver_ptrs, self.S, C.c_void_p(self._ver_last.data_ptr()),
+                                                  C.c_void_p(self._ver_adds.data_ptr()),
+                                                  C.c_void_p(self.staleness_hist.data_ptr()), C.c_int(64),
+                                                  C.c_void_p(N.stream_ptr())), "mvb_stale_on_add")
+
+    def _note_get(self) -> None:
+        if self._ver is not None:
+            N.check(N.cuda_lib().mvb_stale_on_get(self._ver_ptrs, self.S, C.c_void_p(self._ver_last.data_ptr()),
+                                                  C.c_void_p(self._ver_adds.data_ptr()), C.c_void_p(N.stream_ptr())),
+                    "mvb_stale_on_get")
 
     def _opt_box_buf(self):
         """Symmetric option boxes (2 generations x MAX_RANKS AddOptions per rank); allocated at the first
@@ -344,6 +369,7 @@ class DenseDeviceTable(_AsyncOps):
         g.me, g.world, g.ch_done, g.epoch = rt.rank, rt.size, self.ch_done, self.add_epoch
         g.err_flag = rt.err_flag.data_ptr()
         g.timeout_s = float(FLAGS.get("barrier_timeout_s"))
+        self._note_get()        # versions as of the start of the pull (a conservative read point)
         with monitor("WORKER_TABLE_GET", cuda=True, nbytes=self.size * self.esz):
             N.check(lib.mvb_get_dense(C.byref(g), C.c_void_p(N.stream_ptr())), "mvb_get_dense")
         return self._record(), out
@@ -776,7 +802,17 @@ class MatrixDeviceTable(DenseDeviceTable):
 class KVDeviceTable(_AsyncOps):
     """KVTable<K,V>: hash-partitioned map (key % num_servers) as per-shard GPU hash tables.
 
-    ``raw()`` exposes the worker-side cache dict like the reference (kv_table.h:30)."""
+    The reference's server side is an unbounded ``unordered_map`` (kv_table.h:86-106).  Here every shard is an
+    open-addressing table in symmetric HBM that GROWS: at every collective point of the table (``MV_Barrier``,
+    ``reserve``) the ranks agree on the fullest shard's load factor and, above 1/2, every owner re-inserts its
+    shard into a table of twice (or more) the capacity in a freshly allocated symmetric slab; the old slab is
+    released in two phases.  Between two collective points a shard therefore accepts at least as many new keys as it
+    already holds slots in use ("kv-full" is reported by the watchdog if even that is exceeded).
+    ``add`` / ``get`` are asynchronous device operations (no stream synchronisation, no D2H per call): ``get``
+    returns a device tensor; the worker-side cache ``raw()`` (kv_table.h:30) is refreshed lazily from the batches
+    that were pulled."""
+
+    MAX_LOAD = 0.5
 
     def __init__(self, key_dtype="int64", val_dtype="float32", capacity: Optional[int] = None):
         super().__init__()
@@ -787,24 +823,77 @@ class KVDeviceTable(_AsyncOps):
         self.vsz = torch.empty((), dtype=self.vdtype).element_size()
         cap = int(capacity or FLAGS.get("kv_capacity"))
         cap = 1 << (cap - 1).bit_length()
-        self.capacity = cap
         self.S = max(rt.num_servers(), 1)
-        self.keys_buf = rt.alloc_symm(cap * 8)
-        self.vals_buf = rt.alloc_symm(cap * self.vsz)
-        lib = N.cuda_lib()
-        N.check(lib.mvb_kv_init(C.c_void_p(self.keys_buf.local_ptr), C.c_int64(cap),
-                                C.c_void_p(N.stream_ptr())), "mvb_kv_init")
-        self._kv = N.KV()
-        self._kv.vtype, self._kv.nservers, self._kv.capacity = self.vcode, self.S, cap
-        for s in range(self.S):
-            r = rt.server_id_to_rank(s) if rt.num_servers() else rt.rank
-            self._kv.keys[s] = self.keys_buf.ptrs[r]
-            self._kv.vals[s] = self.vals_buf.ptrs[r]
+        self._alloc(cap)
         self._cache: Dict[int, object] = {}
+        self._pending = []                      # (keys, values) device batches not yet folded into the cache
+        self._count = torch.zeros(1, dtype=torch.int64, device=rt.device)
+        self.growths = 0
+        self._added_ub = 0                      # upper bound of the keys this worker may have inserted since the last count
         self.table_id = rt.register_table(self)
+        if rt.size > 1:
+            rt.barrier_hooks.append(self._barrier_hook)
         rt.barrier()
 
+    def _alloc(self, cap: int) -> None:
+        rt, lib = self.rt, N.cuda_lib()
+        self.capacity = cap
+        self.keys_buf = rt.alloc_symm(cap * 8)
+        self.vals_buf = rt.alloc_symm(cap * self.vsz)
+        N.check(lib.mvb_kv_init(C.c_void_p(self.keys_buf.local_ptr), C.c_int64(cap),
+                                C.c_void_p(N.stream_ptr())), "mvb_kv_init")
+        self.vals_buf.tensor(torch.uint8).zero_()
+        kv = N.KV()
+        kv.vtype, kv.nservers, kv.capacity = self.vcode, self.S, cap
+        for s in range(self.S):
+            r = rt.server_id_to_rank(s) if rt.num_servers() else rt.rank
+            kv.keys[s] = self.keys_buf.ptrs[r]
+            kv.vals[s] = self.vals_buf.ptrs[r]
+        self._kv = kv
+
+    # ---- growth -------------------------------------------------------------------------------
+    def live_keys(self) -> int:
+        """Keys stored in this rank's shard (synchronises the stream)."""
+        N.check(N.cuda_lib().mvb_kv_count(C.c_void_p(self.keys_buf.local_ptr), C.c_int64(self.capacity),
+                                          C.c_void_p(self._count.data_ptr()), C.c_void_p(N.stream_ptr())), "mvb_kv_count")
+        return int(self._count.item())
+
+    def reserve(self, keys_per_shard: int = 0) -> None:
+        """Collective: grow every shard until max(load, keys_per_shard / capacity) <= 1/2."""
+        rt, lib = self.rt, N.cuda_lib()
+        torch.cuda.synchronize()
+        live = self.live_keys()
+        self._added_ub = live
+        need = max(rt.all_gather_object(max(live, int(keys_per_shard))))
+        cap = self.capacity
+        while need > self.MAX_LOAD * cap:
+            cap *= 2
+        if cap == self.capacity:
+            return
+        if rt.size > 1:
+            rt.control_barrier()                 # nobody is still pushing into the old slabs
+        old_keys, old_vals, old_cap = self.keys_buf, self.vals_buf, self.capacity
+        self._alloc(cap)
+        N.check(lib.mvb_kv_rehash(self.vcode, C.c_void_p(old_keys.local_ptr), C.c_void_p(old_vals.local_ptr),
+                                  C.c_int64(old_cap), C.c_void_p(self.keys_buf.local_ptr),
+                                  C.c_void_p(self.vals_buf.local_ptr), C.c_int64(cap),
+                                  C.c_void_p(rt.err_flag.data_ptr()), C.c_void_p(N.stream_ptr())), "mvb_kv_rehash")
+        torch.cuda.synchronize()
+        rt.release_symm(old_keys)                # two-phase, collective
+        rt.release_symm(old_vals)
+        self.growths += 1
+        rt.check_watchdog()
+
+    def _barrier_hook(self, final: bool) -> None:
+        if final:
+            self.reserve()
+
+    # ---- ops ----------------------------------------------------------------------------------
     def raw(self) -> Dict[int, object]:
+        for k, v in self._pending:
+            for kk, vv in zip(k.cpu().tolist(), v.cpu().tolist()):
+                self._cache[kk] = vv
+        self._pending = []
         return self._cache
 
     def _keys(self, keys) -> torch.Tensor:
@@ -812,6 +901,8 @@ class KVDeviceTable(_AsyncOps):
         return t.to(self.rt.device).contiguous().view(-1)
 
     def add(self, keys, vals) -> None:
+        """One-sided, asynchronous on the current stream (the reference's Add is a blocking round trip;
+        ``mv.barrier()`` is the completion / visibility point here, as for every async table op)."""
         lib = N.cuda_lib()
         scalar = not hasattr(keys, "__len__") and not torch.is_tensor(keys)
         k = self._keys([keys] if scalar else keys)
@@ -820,20 +911,25 @@ class KVDeviceTable(_AsyncOps):
         N.check(lib.mvb_kv_add(C.byref(self._kv), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()),
                                C.c_int64(k.numel()), C.c_void_p(self.rt.err_flag.data_ptr()),
                                C.c_void_p(N.stream_ptr())), "mvb_kv_add")
-        torch.cuda.current_stream().synchronize()
-        self.rt.check_watchdog()
+        self._keep_add = (k, v)
+        self._added_ub += k.numel()
+        if self.rt.size == 1 and self._added_ub > self.MAX_LOAD * self.capacity:
+            self.reserve()                       # single process: every point is a collective point
 
     def get(self, keys):
+        """Batched lookup; returns a device tensor (a Python scalar for a scalar key)."""
         lib = N.cuda_lib()
         scalar = not hasattr(keys, "__len__") and not torch.is_tensor(keys)
         k = self._keys([keys] if scalar else keys)
         out = torch.empty(k.numel(), dtype=self.vdtype, device=self.rt.device)
         N.check(lib.mvb_kv_get(C.byref(self._kv), C.c_void_p(k.data_ptr()), C.c_void_p(out.data_ptr()),
                                C.c_int64(k.numel()), C.c_void_p(N.stream_ptr())), "mvb_kv_get")
-        host = out.cpu()
-        for kk, vv in zip(k.cpu().tolist(), host.tolist()):
-            self._cache[kk] = vv
-        return host[0].item() if scalar else out
+        self._pending.append((k, out))
+        if len(self._pending) > 64:
+            self.raw()
+        if scalar:
+            return out.cpu()[0].item()
+        return out
 
     def free(self) -> None:
         self.rt.release_symm(self.keys_buf)

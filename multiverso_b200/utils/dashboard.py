@@ -93,6 +93,10 @@ class _Dashboard:
         Log.info("--------------Show dashboard monitor information--------------")
         for name in sorted(self._record):
             Log.info("%s", self._record[name].info_string())
+        for tid, st in self.staleness().items():
+            if st.get("adds"):
+                Log.info("[Staleness] table %s: %d adds, mean %.2f, p50 %d, p99 %d (other workers' adds between "
+                         "my Get and my Add)", tid, st["adds"], st["mean"], st["p50"], st["p99"])
         Log.info("---------------------------------------------------------------")
 
     def snapshot(self) -> dict:
@@ -103,6 +107,37 @@ class _Dashboard:
             out[name] = {"count": m.count, "total_ms": round(m.elapse_ms, 3), "avg_ms": round(m.average(), 4)}
             if m.bytes and m.elapse_ms > 0:
                 out[name]["gbs"] = round(m.bytes / m.elapse_ms / 1e6, 1)
+        return out
+
+    def staleness(self) -> dict:
+        """Staleness histograms of every table created with ``-staleness=true``:
+        {table_id: {"adds": n, "mean": m, "p50": .., "p99": .., "max_bin": .., "hist": [64 bins]}} where bin k counts
+        this worker's shard updates (one per Add and shard) that were applied after k Adds of OTHER workers to that
+        shard since this worker last pulled it (last bin: >= 63)."""
+        from ..runtime import Runtime
+        out = {}
+        rt = Runtime._inst
+        if rt is None:
+            return out
+        for t in getattr(rt, "tables", []):
+            h = getattr(t, "staleness_hist", None)
+            if h is None:
+                continue
+            hist = [int(v) for v in h.cpu().tolist()]
+            n = sum(hist)
+            if n == 0:
+                out[getattr(t, "table_id", len(out))] = {"adds": 0, "hist": hist}
+                continue
+            cum, p50, p99 = 0, None, None
+            for k, v in enumerate(hist):
+                cum += v
+                if p50 is None and cum >= 0.5 * n:
+                    p50 = k
+                if p99 is None and cum >= 0.99 * n:
+                    p99 = k
+            out[getattr(t, "table_id", len(out))] = {
+                "adds": n, "mean": round(sum(k * v for k, v in enumerate(hist)) / n, 3), "p50": p50, "p99": p99,
+                "max_bin": max(k for k, v in enumerate(hist) if v), "hist": hist}
         return out
 
     def reset(self) -> None:

@@ -31,6 +31,7 @@ _DEFAULTS: Dict[str, Any] = {
     "nvls": True,                 # use NVSwitch multicast (multimem.*) for MV_Aggregate when available
     "replicate_get": False,       # BSP ArrayTables: fused Add -> Get (updated shards pushed to replicas);
                                   # measured at 2 GPUs: multimem.st push costs +3.0 ms/GB, a net loss there
+    "staleness": False,           # per-table version counters + staleness histogram (Dashboard.staleness())
     "row_mailbox": True,          # async stateful row Adds: device-side mailboxes + owner-side apply (rowbox.cu)
     "nvls_add": False,            # also reduce dense Adds in the switch (egress-bound either way;
                                   # measured slower than the P2P pull at 2 GPUs: 3.18 vs 1.71 ms)

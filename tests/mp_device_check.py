@@ -156,6 +156,24 @@ def scenario_async():
         sm = 0.5 * sm + 0.5 * 1.0
         dm -= sm
     check("stateful_rows_momentum_mailbox", torch.allclose(mm.get().view(1000, 32)[::2], torch.full((500, 32), dm, device="cuda"), rtol=1e-5))
+    # staleness instrumentation: everybody pulls, then the workers add one after the other -- worker r's Add is
+    # applied after r Adds of other workers since its last Get, a second round sees W - 1 foreign Adds each
+    mv.set_flag("staleness", True)
+    ts_ = mv.ArrayTable(4096, "float32", updater="momentum_sgd")
+    mv.set_flag("staleness", False)
+    ts_.get()
+    for turn in range(2 * W):
+        mv.barrier()
+        if turn % W == r:
+            ts_.add(torch.ones(4096, device="cuda"), mv.AddOption(momentum=0.5))
+            torch.cuda.synchronize()
+    mv.barrier()
+    hist = mv.Dashboard.staleness()[ts_.table_id]["hist"]
+    exp_h = [0] * 64
+    # (one histogram entry per (Add, shard): an Add updates all W shards)
+    exp_h[r] += W                       # first round: r foreign adds since the Get
+    exp_h[W - 1 + r] += W               # second round: no new Get -> foreign adds keep accumulating: (W-1) + r
+    check("staleness_histogram", hist == exp_h, f"{hist[:2 * W + 1]} vs {exp_h[:2 * W + 1]}")
     # KV
     kv = mv.KVTable("int64", "float32")
     keys = torch.arange(0, 1000, device="cuda")

@@ -26,7 +26,12 @@ def _ref_dense(x, labels, w, objective, out):
         p = logits
         loss = 0.5 * ((p - tgt) ** 2).sum()
     grad = (p - tgt).t() @ x.double() / n
-    correct = (p.argmax(1) == labels.long()).sum() if out > 1 else ((p.view(-1) > 0.5) == (labels > 0.5)).sum()
+    if out > 1:
+        correct = (p.argmax(1) == labels.long()).sum()
+    elif objective >= 1:
+        correct = ((p.view(-1) > 0.5) == (labels > 0.5)).sum()
+    else:
+        correct = ((p.view(-1) - labels.double()).abs() < 0.5).sum()
     return loss.item(), int(correct), p.float(), grad.float()
 
 

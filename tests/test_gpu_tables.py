@@ -149,6 +149,28 @@ def test_kv_table(mv_device):
     assert kvi.get(4) == 10**12 + 5
 
 
+def test_kv_table_grows(mv_device):
+    """The reference's server map is unbounded (kv_table.h:86-106): start with 1024 slots, insert 50 000 distinct
+    keys in batches with repeated hits, every value must survive the re-hashes."""
+    import multiverso_b200 as mv
+    kv = mv.KVTable("int64", "float32", capacity=1024)
+    g = torch.Generator().manual_seed(0)
+    keys = torch.randperm(10_000_000, generator=g)[:50_000] - 5_000_000          # negative keys too
+    for lo in range(0, 50_000, 700):
+        k = keys[lo:lo + 700].cuda()
+        kv.add(k, torch.ones(k.numel(), device="cuda"))
+        kv.add(k[:100], torch.full((min(100, k.numel()),), 2.0, device="cuda"))
+    torch.cuda.synchronize()
+    assert kv.growths >= 5 and kv.capacity >= 2 * 50_000
+    got = kv.get(keys.cuda())
+    exp = torch.ones(50_000)
+    for lo in range(0, 50_000, 700):
+        exp[lo:lo + 100] += 2.0
+    assert torch.equal(got.cpu(), exp)
+    assert float(kv.get(123456789)) == 0.0                                        # missing key -> default value
+    assert kv.live_keys() == 50_000
+
+
 def test_aggregate_single_rank(mv_device):
     x = torch.ones(10, device="cuda")
     mv_device.aggregate(x)
