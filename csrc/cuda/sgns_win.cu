@@ -158,6 +158,63 @@ MVB_DEVINL void sts_f4(unsigned char* p, F4 v) {
   *reinterpret_cast<float4*>(p) = make_float4(v.lo.x, v.lo.y, v.hi.x, v.hi.y);
 }
 
+// A row of `dim` floats spread over the 32 lanes of a warp: NF4 chunks of one float4 per lane (the last
+// one possibly partial) and, when 16 or fewer float4 remain (dim 300: 11), a TAIL of one float2 per lane over twice
+// as many lanes instead of a half-empty float4 chunk -- 10 registers and 5 FFMA2 per 300-float row and dot
+// instead of 12 and 6.
+template <int NF4, bool TAIL>
+struct Row {
+  F4 v[NF4 > 0 ? NF4 : 1];
+  float2 t;
+};
+struct RowAct {
+  bool v[4];       // lane holds a float4 of chunk j
+  bool t;          // lane holds a float2 of the tail
+  int tail_off;    // byte offset of the tail inside a row
+};
+template <int NF4, bool TAIL>
+MVB_DEVINL void row_zero(Row<NF4, TAIL>& r) {
+#pragma unroll
+  for (int j = 0; j < NF4; ++j) r.v[j].lo = r.v[j].hi = make_float2(0.f, 0.f);
+  r.t = make_float2(0.f, 0.f);
+}
+template <int NF4, bool TAIL>
+MVB_DEVINL void row_load(Row<NF4, TAIL>& r, const unsigned char* base, int lane, const RowAct& act) {
+  row_zero(r);
+#pragma unroll
+  for (int j = 0; j < NF4; ++j)
+    if (act.v[j]) r.v[j] = lds_f4(base + (size_t)(lane + 32 * j) * 16);
+  if (TAIL && act.t) r.t = *reinterpret_cast<const float2*>(base + act.tail_off + lane * 8);
+}
+template <int NF4, bool TAIL>
+MVB_DEVINL void row_store(unsigned char* base, const Row<NF4, TAIL>& r, int lane, const RowAct& act) {
+#pragma unroll
+  for (int j = 0; j < NF4; ++j)
+    if (act.v[j]) sts_f4(base + (size_t)(lane + 32 * j) * 16, r.v[j]);
+  if (TAIL && act.t) *reinterpret_cast<float2*>(base + act.tail_off + lane * 8) = r.t;
+}
+template <int NF4, bool TAIL>
+MVB_DEVINL float row_dot(const Row<NF4, TAIL>& x, const Row<NF4, TAIL>& y) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NF4; ++j) {
+    acc = ffma2(x.v[j].lo, y.v[j].lo, acc);
+    acc = ffma2(x.v[j].hi, y.v[j].hi, acc);
+  }
+  if (TAIL) acc = ffma2(x.t, y.t, acc);
+  return acc.x + acc.y;
+}
+template <int NF4, bool TAIL>
+MVB_DEVINL void row_axpy(Row<NF4, TAIL>& y, float g, const Row<NF4, TAIL>& x) {       // y += g * x
+  const float2 gg = make_float2(g, g);
+#pragma unroll
+  for (int j = 0; j < NF4; ++j) {
+    y.v[j].lo = ffma2(gg, x.v[j].lo, y.v[j].lo);
+    y.v[j].hi = ffma2(gg, x.v[j].hi, y.v[j].hi);
+  }
+  if (TAIL) y.t = ffma2(gg, x.t, y.t);
+}
+
 // smem carve-up (all offsets from the dynamic smem base, which is 128-byte aligned)
 struct Layout {
   int in_full, in_empty, out_full, out_empty;   // mbarrier arrays (byte offsets)
@@ -188,9 +245,10 @@ __host__ __device__ inline Layout make_layout(int ring, int nw, int ko, int row_
   return L;
 }
 
-template <int VPL, int KO>
+template <int NF4, bool TAIL, int KO>
 __global__ void __launch_bounds__(kThreads, 1)
 sgns_win_kernel(const __grid_constant__ WinDev a) {
+  using RowT = Row<NF4, TAIL>;
   extern __shared__ __align__(128) unsigned char smem[];
   const Layout L = make_layout(a.ring, a.nw, a.ko, a.row_bytes);
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + L.in_full);
@@ -390,9 +448,14 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
   float loss_acc = 0.f;
   unsigned long long pairs_acc = 0ull;
   uint32_t din_count = 0;
-  bool lane_act[VPL];
+  RowAct act;
+  {
+    const int full4 = TAIL ? NF4 * 32 : nvec;            // float4s covered by the float4 chunks
 #pragma unroll
-  for (int j = 0; j < VPL; ++j) lane_act[j] = (lane + 32 * j) < nvec;
+    for (int j = 0; j < 4; ++j) act.v[j] = j < NF4 && (lane + 32 * j) < full4;
+    act.tail_off = NF4 * 512;
+    act.t = TAIL && lane < 2 * (nvec - NF4 * 32);
+  }
 
   int64_t n = 0;
   for (int64_t i = cw;; i += NW, ++n) {
@@ -441,15 +504,11 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
       }
       if (ctx) {
         // ---- phase 1: output rows in registers, per context dots + input-row delta -------------
-        F4 O[KO][VPL];
+        RowT O[KO];
 #pragma unroll
         for (int k = 0; k < KO; ++k) {
-#pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            O[k][j].lo = O[k][j].hi = make_float2(0.f, 0.f);
-            if (((used >> k) & 1u) && lane_act[j])
-              O[k][j] = lds_f4(rows + (size_t)k * a.row_bytes + (size_t)(lane + 32 * j) * 16);
-          }
+          row_zero(O[k]);
+          if ((used >> k) & 1u) row_load(O[k], rows + (size_t)k * a.row_bytes, lane, act);
         }
         float gs[KO];                                   // lane t keeps the error terms of context t
 #pragma unroll
@@ -460,54 +519,58 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
           const int slot = __shfl_sync(0xffffffffu, cslot, t);
           float* gptr = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)cptr, t));
           const float isc = __shfl_sync(0xffffffffu, csc, t);
-          const unsigned char* hrow = in_rows + (size_t)slot * a.row_bytes;
-          F4 h[VPL];
+          RowT h;
+          row_load(h, in_rows + (size_t)slot * a.row_bytes, lane, act);
+          // 1+K dots; the 8 partial sums are reduced together: three exchange steps halve the number of
+          // live values (lanes keep the half they will own), two more finish -> 9 shuffles instead of 5 per dot
+          float f8[8];
 #pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            h[j].lo = h[j].hi = make_float2(0.f, 0.f);
-            if (lane_act[j]) h[j] = lds_f4(hrow + (size_t)(lane + 32 * j) * 16);
-          }
-          float f[KO];
+          for (int k = 0; k < 8; ++k) f8[k] = k < KO ? row_dot(h, O[k]) : 0.f;
+          {
+            const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+            float f4[4], f2[2], f1;
 #pragma unroll
-          for (int k = 0; k < KO; ++k) {
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-              acc = ffma2(h[j].lo, O[k][j].lo, acc);
-              acc = ffma2(h[j].hi, O[k][j].hi, acc);
+            for (int k = 0; k < 4; ++k) {
+              const float send = up16 ? f8[k] : f8[k + 4];
+              const float keep = up16 ? f8[k + 4] : f8[k];
+              f4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
-            f[k] = acc.x + acc.y;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float send = up8 ? f4[k] : f4[k + 2];
+              const float keep = up8 ? f4[k + 2] : f4[k];
+              f2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+              const float send = up4 ? f2[0] : f2[1];
+              const float keep = up4 ? f2[1] : f2[0];
+              f1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            f1 += __shfl_xor_sync(0xffffffffu, f1, 2);
+            f1 += __shfl_xor_sync(0xffffffffu, f1, 1);
+            // lane L now holds the full dot of output row k(L) = 4*[L&16] + 2*[L&8] + [L&4]
+            const int myk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            const bool u = (used >> myk) & 1u;
+            const float gmine = u ? ((myk == 0 ? 1.f : 0.f) - sigm_fast(f1)) * a.lr : 0.f;
+            if (want_loss && u && (lane & 3) == 0) loss_acc += 8.f * softplus_neg(myk == 0 ? f1 : -f1);
+            // lane holding row k: (k&4 ? 16 : 0) + (k&2 ? 8 : 0) + (k&1 ? 4 : 0)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              f8[k] = __shfl_sync(0xffffffffu, gmine, ((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4);
           }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < KO; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], o);
-          }
-          float g[KO];
-#pragma unroll
-          for (int k = 0; k < KO; ++k) {
-            const bool u = (used >> k) & 1u;
-            g[k] = u ? ((k == 0 ? 1.f : 0.f) - sigm_fast(f[k])) * a.lr : 0.f;
-            if (want_loss && u) loss_acc += 8.f * softplus_neg(k == 0 ? f[k] : -f[k]);
-            if (lane == t) gs[k] = g[k];
-          }
+          for (int k = 0; k < KO; ++k)
+            if (lane == t) gs[k] = f8[k];
           // input-row delta of this context -> staging ring -> one bulk reduction
           unsigned char* dst = my_din + (size_t)(din_count % kDinSlots) * a.row_bytes;
           ++din_count;
           if (lane == 0) bulk_wait_read<kDinSlots - 1>();   // the slot's previous reduction has read it
           __syncwarp();
+          RowT e;
+          row_zero(e);
 #pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            F4 e;
-            e.lo = e.hi = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < KO; ++k) {
-              const float2 gg = make_float2(g[k] * isc, g[k] * isc);
-              e.lo = ffma2(gg, O[k][j].lo, e.lo);
-              e.hi = ffma2(gg, O[k][j].hi, e.hi);
-            }
-            if (lane_act[j]) sts_f4(dst + (size_t)(lane + 32 * j) * 16, e);
-          }
+          for (int k = 0; k < KO; ++k) row_axpy(e, f8[k] * isc, O[k]);
+          row_store(dst, e, lane, act);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -518,38 +581,21 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
         }
         // ---- phase 2: output-row deltas sum_c g_ck * in_c accumulate in registers ----------------
 #pragma unroll
-        for (int k = 0; k < KO; ++k)
-#pragma unroll
-          for (int j = 0; j < VPL; ++j) O[k][j].lo = O[k][j].hi = make_float2(0.f, 0.f);
+        for (int k = 0; k < KO; ++k) row_zero(O[k]);
         for (uint32_t m = ctx; m; m &= m - 1) {
           const int t = __ffs(m) - 1;
           const int slot = __shfl_sync(0xffffffffu, cslot, t);
-          const unsigned char* hrow = in_rows + (size_t)slot * a.row_bytes;
-          F4 h[VPL];
-#pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            h[j].lo = h[j].hi = make_float2(0.f, 0.f);
-            if (lane_act[j]) h[j] = lds_f4(hrow + (size_t)(lane + 32 * j) * 16);
-          }
+          RowT h;
+          row_load(h, in_rows + (size_t)slot * a.row_bytes, lane, act);
 #pragma unroll
           for (int k = 0; k < KO; ++k) {
             const float gk = __shfl_sync(0xffffffffu, gs[k], t) * __shfl_sync(0xffffffffu, my_osc, k);
-            const float2 gg = make_float2(gk, gk);
-#pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-              O[k][j].lo = ffma2(gg, h[j].lo, O[k][j].lo);
-              O[k][j].hi = ffma2(gg, h[j].hi, O[k][j].hi);
-            }
+            row_axpy(O[k], gk, h);
           }
         }
 #pragma unroll
-        for (int k = 0; k < KO; ++k) {
-          if ((used >> k) & 1u) {
-#pragma unroll
-            for (int j = 0; j < VPL; ++j)
-              if (lane_act[j]) sts_f4(rows + (size_t)k * a.row_bytes + (size_t)(lane + 32 * j) * 16, O[k][j]);
-          }
-        }
+        for (int k = 0; k < KO; ++k)
+          if ((used >> k) & 1u) row_store(rows + (size_t)k * a.row_bytes, O[k], lane, act);
         fence_proxy_async();
         __syncwarp();
         if (lane < KO && my_ptr != nullptr) {
@@ -566,6 +612,8 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
     }
   }
   if (lane < kRelLanes) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // adds performed
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);   // lanes hold different rows
   if (lane == 0) {
     if (a.loss_sum && loss_acc != 0.f) atomicAdd(a.loss_sum, loss_acc);
     if (a.pair_count && pairs_acc) atomicAdd(a.pair_count, pairs_acc);
@@ -647,29 +695,35 @@ extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream) {
   }
   const int64_t n_chunks = (h->n_tokens + a.chunk - 1) / a.chunk;
   if ((int64_t)blocks > n_chunks) blocks = (int)n_chunks;
-  const int vpl = (h->dim / 4 + 31) / 32;
+  // register layout of a row: full float4 chunks (+ a partial one) or a float2 tail (Row<NF4, TAIL>)
+  const int nvec = h->dim / 4, fc = nvec / 32, rem4 = nvec % 32;
+  int nf4 = fc, tail = 0;
+  if (rem4 > 16) nf4 = fc + 1;
+  else if (rem4 > 0) tail = 1;
   const size_t smem = (size_t)L.total;
-#define MVB_LAUNCH_WIN(V, K)                                                                         \
+#define MVB_LAUNCH_WIN(NF, TL, K)                                                                    \
   do {                                                                                               \
-    MVB_CUDA_CHECK(cudaFuncSetAttribute(sgns_win_kernel<V, K>,                                       \
+    MVB_CUDA_CHECK(cudaFuncSetAttribute(sgns_win_kernel<NF, TL, K>,                                  \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    sgns_win_kernel<V, K><<<blocks, kThreads, smem, st>>>(a);                                        \
+    sgns_win_kernel<NF, TL, K><<<blocks, kThreads, smem, st>>>(a);                                   \
   } while (0)
-  if (a.ko <= 6) {
-    switch (vpl) {
-      case 1: MVB_LAUNCH_WIN(1, 6); break;
-      case 2: MVB_LAUNCH_WIN(2, 6); break;
-      case 3: MVB_LAUNCH_WIN(3, 6); break;
-      default: MVB_LAUNCH_WIN(4, 6); break;
-    }
-  } else {
-    switch (vpl) {
-      case 1: MVB_LAUNCH_WIN(1, 8); break;
-      case 2: MVB_LAUNCH_WIN(2, 8); break;
-      case 3: MVB_LAUNCH_WIN(3, 8); break;
-      default: MVB_LAUNCH_WIN(4, 8); break;
-    }
-  }
+#define MVB_DISPATCH_WIN(K)                                                  \
+  do {                                                                       \
+    switch (nf4 * 2 + tail) {                                                \
+      case 1: MVB_LAUNCH_WIN(0, true, K); break;                             \
+      case 2: MVB_LAUNCH_WIN(1, false, K); break;                            \
+      case 3: MVB_LAUNCH_WIN(1, true, K); break;                             \
+      case 4: MVB_LAUNCH_WIN(2, false, K); break;                            \
+      case 5: MVB_LAUNCH_WIN(2, true, K); break;                             \
+      case 6: MVB_LAUNCH_WIN(3, false, K); break;                            \
+      case 7: MVB_LAUNCH_WIN(3, true, K); break;                             \
+      case 8: MVB_LAUNCH_WIN(4, false, K); break;                            \
+      default: return -21;                                                   \
+    }                                                                        \
+  } while (0)
+  if (a.ko <= 6) MVB_DISPATCH_WIN(6);
+  else MVB_DISPATCH_WIN(8);
+#undef MVB_DISPATCH_WIN
 #undef MVB_LAUNCH_WIN
   MVB_CUDA_CHECK(cudaGetLastError());
   return 0;
