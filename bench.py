@@ -446,14 +446,17 @@ def table_bandwidth(mv, torch, world):
             n = 5
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for it in range(n):
+            handles = []
+            for it in range(n):                      # enqueue back to back: device time, not host round trips
                 if name == "add":
-                    t.wait(t.add_async(delta, staged=world > 1))
+                    handles.append(t.add_async(delta, staged=world > 1))
                     if world > 1:
                         delta = t.staging()
                 else:
-                    t.get(buf)
+                    handles.append(t.get_async(buf)[0])
             e1.record()
+            for h in handles:
+                t.wait(h)
             torch.cuda.synchronize()
             ms = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device="cuda")
             if world > 1:

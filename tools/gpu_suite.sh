@@ -120,6 +120,16 @@ r2n8)
     MVB_GET_BULK=$v timeout 300 $L bench/matrix_bw.py > gpurun_out/matrix_bw_bulk${v}_n$NG.log 2>&1; echo "matrix_bw MVB_GET_BULK=$v rc=$?"; grep '^{' gpurun_out/matrix_bw_bulk${v}_n$NG.log | tail -1 | cut -c1-700
   done
   ;;
+r2final)
+  # round 2 final multi-GPU call: bulk Add correctness + timing, config-5 stress, headline bench
+  MVB_ADD_BULK=2 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+30)) tests/mp_device_check.py sync > gpurun_out/mp_check_sync_addbulk_n$NG.log 2>&1; echo "mp sync (bulk add) rc=$?"; grep -cE "PASS" gpurun_out/mp_check_sync_addbulk_n$NG.log; grep -E "FAIL|Error" gpurun_out/mp_check_sync_addbulk_n$NG.log | head -3 | cut -c1-400
+  L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+31))"
+  for v in 0 1; do
+    MVB_ADD_BULK=$v timeout 300 $L bench/matrix_bw.py > gpurun_out/matrix_bw_addbulk${v}_n$NG.log 2>&1; echo "matrix_bw MVB_ADD_BULK=$v rc=$?"; grep '^{' gpurun_out/matrix_bw_addbulk${v}_n$NG.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:round(v,3) for k,v in d.items() if k.endswith('_ms')})"
+  done
+  timeout 400 $L bench/array_async_stress.py > gpurun_out/array_async_stress_n$NG.log 2>&1; echo "stress rc=$?"; grep '^{' gpurun_out/array_async_stress_n$NG.log | tail -1 | cut -c1-900
+  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((PORT+32)) bench.py --gpus $NG --steps 20 --warmup 5 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err; echo "bench$NG rc=$?"; grep '^{' gpurun_out/bench_n$NG.json | cut -c1-400; tail -3 gpurun_out/bench_n$NG.err
+  ;;
 refarm)
   timeout 1500 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_n1.json
   ;;
