@@ -286,6 +286,20 @@ int mvb_sgns_train(const MvbSgns* a, void* stream);
 int mvb_sgns_train_tma(const MvbSgns* a, void* stream);   /* TMA bulk-copy pipeline variant */
 int mvb_sgns_train_win(const MvbSgns* a, void* stream);   /* window-batched TMA pipeline      */
 int mvb_sgns_win_inflight(int dim, int negative, int window, int max_ctas);  /* centre positions in flight */
+/* ---- key-addressed shards for application-defined tables (keys.cu): the device-side extension point ---- */
+typedef struct MvbKeyMap {
+  int64_t size;                        /* keys 0 .. size-1                                   */
+  int64_t per_server;                  /* size / nservers, the last server takes the remainder */
+  int nservers;
+  int width;                           /* fp32 values per key (SparseTable 1, FTRLTable 2)    */
+  void* shard_ptrs[MVB_MAX_RANKS];     /* server s: [keys of s x width] fp32, peer mapped      */
+  void* touched_ptrs[MVB_MAX_RANKS];   /* server s: touched bitmap uint32[ceil(keys of s / 32)] */
+} MvbKeyMap;
+int mvb_keys_add(const MvbKeyMap* m, const int64_t* keys, const float* vals, int64_t n, float sign, void* stream);
+int mvb_keys_get(const MvbKeyMap* m, const int64_t* keys, float* out, int64_t n, void* stream);
+int mvb_keys_collect(const MvbKeyMap* m, int64_t* out_keys, float* out_vals, int64_t* count, int64_t cap,
+                     void* stream);
+
 /* ---- staleness instrumentation: per-shard version counters (symmetric memory), bumped by every Add,
    recorded by every Get; staleness of an Add = other workers' Adds applied since this worker's last Get */
 int mvb_stale_on_add(void* const* version_ptrs, int nservers, unsigned long long* last_get,

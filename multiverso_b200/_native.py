@@ -95,6 +95,11 @@ class Sgns(C.Structure):
     ]
 
 
+class KeyMap(C.Structure):
+    _fields_ = [("size", i64), ("per_server", i64), ("nservers", C.c_int), ("width", C.c_int),
+                ("shard_ptrs", VP8), ("touched_ptrs", VP8)]
+
+
 class RowBox(C.Structure):
     _fields_ = [
         ("map", RowMap), ("me", C.c_int), ("cap", i64), ("slot_bytes", i64), ("box", VP8), ("ack", VP8),

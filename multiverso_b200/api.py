@@ -109,8 +109,11 @@ def net_finalize() -> None:
 
 def save_table(table, uri: str) -> bool:
     """MV_SaveTable: every server writes its shard of ``table`` (and the updater state) to
-    ``<uri>.shard<server_id>``; collective, ends with a barrier.  Same naming and byte layout
-    (raw shard dump, then the state slabs) on both backends."""
+    ``<uri>.shard<server_id>``; collective, ends with a barrier.  Layout: the raw shard dump (which is
+    all the reference writes, array_table.cpp:143-151) followed by the updater state slabs.  Files of
+    stateless tables are interchangeable between the host and the device backend; for stateful updaters the
+    device pads the per-worker state stride to a multiple of 4 elements, so those checkpoints must be loaded
+    by the backend (and the number of servers) that wrote them."""
     rt = _rt()
     if rt.backend == "host":
         return bool(table.store(uri))

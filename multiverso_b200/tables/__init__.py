@@ -57,9 +57,23 @@ def create_table(option):
         return ArrayTable(option.size, option.dtype)
     if isinstance(option, KVTableOption):
         return KVTable(option.key_dtype, option.val_dtype)
+    if hasattr(option, "create"):
+        # application-defined table types (DEFINE_TABLE_TYPE, table_interface.h:77-80): the option knows its table
+        return option.create()
     raise TypeError(f"unknown table option {type(option)}")
 
 
-__all__ = ["ArrayTable", "MatrixTable", "SparseMatrixTable", "KVTable", "create_table", "AddOption",
+def SparseTable(size, width=1):
+    """LogisticRegression's application table (sparse_table.h) on the device extension point."""
+    from .custom import SparseDeviceTable
+    return SparseDeviceTable(size, width)
+
+
+def FTRLTable(size):
+    from .custom import FTRLDeviceTable
+    return FTRLDeviceTable(size)
+
+
+__all__ = ["SparseTable", "FTRLTable", "ArrayTable", "MatrixTable", "SparseMatrixTable", "KVTable", "create_table", "AddOption",
            "GetOption", "ArrayTableOption", "MatrixTableOption", "MatrixOption",
            "SparseMatrixTableOption", "KVTableOption"]

@@ -174,6 +174,21 @@ def scenario_async():
     exp_h[r] += W                       # first round: r foreign adds since the Get
     exp_h[W - 1 + r] += W               # second round: no new Get -> foreign adds keep accumulating: (W-1) + r
     check("staleness_histogram", hist == exp_h, f"{hist[:2 * W + 1]} vs {exp_h[:2 * W + 1]}")
+    # application-defined tables on the device extension point (LogReg's SparseTable / FTRLTable): keys of every
+    # owner, server subtracts, whole-table Get returns the union of the keys anybody wrote
+    from multiverso_b200.tables.custom import SparseDeviceTable
+    spt = SparseDeviceTable(100003)
+    skeys = torch.arange(r, 100003, 11, device="cuda")
+    spt.add(skeys, torch.full((skeys.numel(),), float(r + 1), device="cuda"))
+    torch.cuda.synchronize(); mv.barrier()
+    exp_keys = torch.unique(torch.cat([torch.arange(w, 100003, 11) for w in range(W)]))
+    dense = torch.zeros(100003)
+    for w in range(W):
+        dense[torch.arange(w, 100003, 11)] -= (w + 1)
+    ka, va = spt.get()
+    check("app_sparse_table", torch.equal(ka.cpu(), exp_keys) and torch.equal(va.cpu(), dense[exp_keys])
+          and torch.equal(spt.get(skeys).cpu(), dense[skeys.cpu()]))
+    mv.barrier()
     # KV
     kv = mv.KVTable("int64", "float32")
     keys = torch.arange(0, 1000, device="cuda")

@@ -171,6 +171,71 @@ def test_kv_table_grows(mv_device):
     assert kv.live_keys() == 50_000
 
 
+def test_app_defined_tables_sparse_and_ftrl(mv_device):
+    """The reference's application tables (sparse_table.h, ftrl_sparse_table.h) on the device extension point:
+    server subtracts, whole-table Get returns only the keys ever written, FTRL carries {z, n} pairs."""
+    import multiverso_b200 as mv
+    from multiverso_b200.tables.custom import SparseTableOption, FTRLDeviceTable
+    n = 1_000_003
+    t = mv.create_table(SparseTableOption(n))
+    g = torch.Generator().manual_seed(0)
+    keys = torch.randperm(n, generator=g)[:5000]
+    vals = torch.randn(5000, generator=g)
+    t.add(keys, vals)
+    t.add(keys[:100], torch.ones(100))
+    exp = -vals.clone(); exp[:100] -= 1.0
+    assert torch.allclose(t.get(keys).cpu(), exp, atol=1e-6)
+    assert float(t.get([n - 1 if (n - 1) not in keys.tolist() else 7]).abs().sum()) >= 0.0
+    k_all, v_all = t.get()
+    order = torch.argsort(keys)
+    assert torch.equal(k_all.cpu(), keys[order]) and torch.allclose(v_all.cpu(), exp[order], atol=1e-6)
+    f = FTRLDeviceTable(4099)
+    fk = torch.arange(0, 4099, 7)
+    f.add(fk, torch.stack([torch.full((fk.numel(),), 0.5), torch.full((fk.numel(),), 2.0)], 1))
+    got = f.get(fk).cpu()
+    assert torch.allclose(got[:, 0], torch.full((fk.numel(),), -0.5)) and torch.allclose(got[:, 1], torch.full((fk.numel(),), -2.0))
+    ka, va = f.get()
+    assert ka.numel() == fk.numel() and va.shape == (fk.numel(), 2)
+
+
+def test_custom_device_table_extension_point(mv_device, tmp_path):
+    """A user-defined table on the extension point: subclass CustomDeviceTable, express the ops on the peer-mapped
+    shard tensors, get table id / partition / checkpoint plumbing from the base."""
+    import multiverso_b200 as mv
+    from multiverso_b200.tables.custom import CustomDeviceTable
+
+    class MaxTable(CustomDeviceTable):                     # Add keeps the element-wise maximum
+        def __init__(self, size):
+            super().__init__(size, 4)
+
+        def add(self, keys, vals):
+            keys = torch.as_tensor(keys, device="cuda"); vals = torch.as_tensor(vals, dtype=torch.float32, device="cuda")
+            for s in range(self.S):
+                m = (keys >= self.lo[s]) & (keys < self.hi[s])
+                if bool(m.any()):
+                    shard = self.peer_tensor(s)
+                    idx = keys[m] - self.lo[s]
+                    shard[idx] = torch.maximum(shard[idx], vals[m])
+
+        def get(self, keys):
+            keys = torch.as_tensor(keys, device="cuda")
+            out = torch.empty(keys.numel(), device="cuda")
+            for s in range(self.S):
+                m = (keys >= self.lo[s]) & (keys < self.hi[s])
+                if bool(m.any()):
+                    out[m] = self.peer_tensor(s)[keys[m] - self.lo[s]]
+            return out
+
+    t = MaxTable(1000)
+    t.add([1, 5, 999], [3.0, -1.0, 7.0])
+    t.add([1, 5], [2.0, 4.0])
+    assert t.get([1, 5, 999, 0]).tolist() == [3.0, 4.0, 7.0, 0.0]
+    assert mv.save_table(t, str(tmp_path / "max"))
+    t.add([1], [100.0])
+    assert mv.load_table(t, str(tmp_path / "max"))
+    assert t.get([1]).tolist() == [3.0]
+
+
 def test_aggregate_single_rank(mv_device):
     x = torch.ones(10, device="cuda")
     mv_device.aggregate(x)
