@@ -266,6 +266,10 @@ def main():
     sync_all()
     we._prefetched = None
     E2E_WARM = 2                                     # untimed iterations of the SAME loop (pipeline primed)
+    # debugging knobs (never set for a reported number): which part of the e2e loop costs what
+    DBG_NO_H2D = os.environ.get("BENCH_E2E_NO_H2D") == "1"
+    DBG_NO_D2H = os.environ.get("BENCH_E2E_NO_D2H") == "1"
+    DBG_NO_SYNC = os.environ.get("BENCH_E2E_NO_SYNC") == "1"
     tok2 = [tok_dev, torch.empty_like(tok_dev)]
     loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
@@ -296,7 +300,8 @@ def main():
         # buffer was last read by block i-1, i.e. before `done_ev`
         copy_stream.wait_event(done_ev)
         with torch.cuda.stream(copy_stream):
-            nxt.copy_(pinned[W + (i + 1) % K], non_blocking=True)
+            if not DBG_NO_H2D:
+                nxt.copy_(pinned[W + (i + 1) % K], non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(copy_stream)
         main_stream.wait_event(cur_copied)           # this step's tokens are on the device
@@ -304,7 +309,8 @@ def main():
             we.train_block(cur, compute_loss=True, next_tokens=nxt, next_ready=copied)
         else:
             we.train_block(cur, compute_loss=True)
-        loss_pin[i % 2].copy_(we.loss, non_blocking=True)        # D2H of the step's result
+        if not DBG_NO_D2H:
+            loss_pin[i % 2].copy_(we.loss, non_blocking=True)    # D2H of the step's result
         loss_ev[i % 2].record()
         if i >= 0:
             step_ev[i + 1].record()
@@ -313,14 +319,14 @@ def main():
         else:
             done_ev = torch.cuda.Event()
             done_ev.record()
-        if i > 0:                                                # consume step i-1's loss on the host
+        if i > 0 and not DBG_NO_SYNC:                            # consume step i-1's loss on the host
             loss_ev[(i - 1) % 2].synchronize()
             losses_host.append(float(loss_pin[(i - 1) % 2]))
     loss_ev[(we2_steps - 1) % 2].synchronize()
     losses_host.append(float(loss_pin[(we2_steps - 1) % 2]))
     torch.cuda.synchronize()
     e2e_s_local = time.perf_counter() - t0
-    assert len(losses_host) == we2_steps and all(l == l for l in losses_host)
+    assert DBG_NO_SYNC or (len(losses_host) == we2_steps and all(l == l for l in losses_host))
     e2e_trace = {"gpu_step_ms": [round(step_ev[i].elapsed_time(step_ev[i + 1]), 2) for i in range(we2_steps)],
                  "host_enqueue_done_ms": [round(t * 1e3, 2) for t in host_t],
                  "total_ms": round(e2e_s_local * 1e3, 2)}

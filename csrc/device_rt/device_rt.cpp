@@ -354,6 +354,7 @@ struct DenseTable<T>::Impl : Registered {
   int64_t state_stride = 0;
   std::vector<void*> shard_ptrs;                    // by server id
   std::unique_ptr<SymmBuffer> stage[2];             // double-buffered full-table staging (collective Adds)
+  std::unique_ptr<SymmBuffer> opt_box;              // per-worker AddOptions of the collective Add (2 generations)
   int stage_idx = 0;
   SymmBuffer* cur_stage = nullptr;
   int ch_ready = 0, ch_done = 0;
@@ -402,6 +403,11 @@ struct DenseTable<T>::Impl : Registered {
     }
     a.scale = 1.0f;
     a.clip = 0.0f;
+    // the AddOption travels with the request: this worker's option is published in every owner's option box
+    // inside the kernel, owners apply worker w's delta with worker w's option (reference: last Blob of Request_Add)
+    a.my_worker = c.size > 1 ? MV_WorkerId() : 0;
+    if (use_pads && opt_box)
+      for (int r = 0; r < c.size; ++r) a.opt_box[r] = opt_box->peer(r);
     a.pads = use_pads ? c.pads->ptrs() : nullptr;
     a.me = c.rank;
     a.world = c.size;
@@ -532,6 +538,10 @@ DenseTable<T>::DenseTable(int64_t num_row, int64_t num_col, const TableInit& ini
   const int64_t slab = m.state_stride * (m.upd->per_worker ? m.W : 1);
   for (int i = 0; i < m.upd->n_states; ++i)
     m.state.emplace_back(new SymmBuffer(std::max<int64_t>(slab, 1) * sizeof(T)));
+  if (c.size > 1 && m.sync) {
+    m.opt_box.reset(new SymmBuffer(2 * MVB_MAX_RANKS * 32));
+    MVB_CHECK(mvb_memset_async(m.opt_box->local(), 0, 2 * MVB_MAX_RANKS * 32, nullptr));
+  }
   m.ch_ready = c.NewChannels(2);
   m.ch_done = m.ch_ready + 1;
   m.done_counter = c.NewCounter();

@@ -241,6 +241,31 @@ static void TestUpdaters() {
   }
 }
 
+// The AddOption travels with each worker's request: per-worker learning rates under AdaGrad (per-worker
+// history).  Worker w adds delta = lr_w twice; the owner moves every element by rho/sqrt(1) + rho/sqrt(2) per
+// worker only if it divides worker w's delta by worker w's OWN learning rate.
+static void TestPerWorkerOption() {
+  const int W = MV_NumWorkers();
+  const int64_t n = 2053;
+  dev::ArrayTable<float> table(n, dev::TableInit::Fill(0.0), "adagrad");
+  const float lr = 0.01f * static_cast<float>(MV_WorkerId() + 1);
+  AddOption opt;
+  opt.set_learning_rate(lr);
+  opt.set_rho(0.1f);
+  std::vector<float> delta(n, lr);
+  DeviceArray<float> d(n), out(n);
+  d.Upload(delta);
+  for (int step = 0; step < 2; ++step) AddFromEveryWorker(&table, d.ptr, &opt);
+  dev::Barrier();
+  table.Get(out.ptr);
+  const std::vector<float> got = out.Download();
+  const double e = -W * (0.1 / std::sqrt(1.0 + 1e-6) + 0.1 / std::sqrt(2.0 + 1e-6));
+  double worst = 0;
+  for (int64_t i = 0; i < n; ++i) worst = std::max(worst, std::fabs(got[i] - e));
+  EXPECT(worst < 1e-3);
+  dev::Barrier();
+}
+
 static void TestCheckpoint() {
   const int64_t n = 1000;
   dev::ArrayTable<float> table(n, dev::TableInit::Uniform(-1, 1, 7), "momentum_sgd");
@@ -329,6 +354,7 @@ int main(int argc, char* argv[]) {
   if (all || which == "kv") TestKV();
   if (all || which == "aggregate") TestAggregate();
   if (all || which == "updaters") TestUpdaters();
+  if (all || which == "peropt") TestPerWorkerOption();
   if (all || which == "checkpoint") TestCheckpoint();
   if (which == "bench") BenchMatrix(argc > 2 ? atoll(argv[2]) : 1000000);
   dev::Barrier();
