@@ -241,6 +241,9 @@ def main():
     launches0 = we.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
+    trace_dev = os.environ.get("BENCH_TRACE") == "1" and world > 1
+    if trace_dev:
+        we.trace = []
     ev0.record()
     for i in range(K):
         step_device(W + i)
@@ -248,6 +251,12 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     sampler.mark_end()
+    device_trace = None
+    if trace_dev:
+        tr, we.trace = we.trace, None
+        device_trace = {"k7_ms": [round(a.elapsed_time(b), 3) for a, b in tr],
+                        "gap_ms": [round(tr[j][1].elapsed_time(tr[j + 1][0]), 3) for j in range(len(tr) - 1)],
+                        "first_start_ms": round(ev0.elapsed_time(tr[0][0]), 3), "tail_ms": round(tr[-1][1].elapsed_time(ev1), 3)}
     ms_local = ev0.elapsed_time(ev1)
     launches = we.kernel_launches - launches0
     sync_all()
@@ -363,7 +372,8 @@ def main():
                             "step i is step i+1's) and D2H of the step's loss into pinned host memory, consumed on the host "
                             "during step i+1; 2 untimed warm-up iterations of the same loop"},
             "gpu_launches": launches,
-            "extra": dict(extra, monitors_device_arm=monitors, e2e_trace_rank0=e2e_trace),
+            "extra": dict(extra, monitors_device_arm=monitors, e2e_trace_rank0=e2e_trace,
+                          **({"device_trace_rank0": device_trace} if device_trace else {})),
         }
         if "get_plus_add_gbs" in extra:
             # second half of the BASELINE.json metric, same key in the reference arm's line

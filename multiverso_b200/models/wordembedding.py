@@ -450,6 +450,17 @@ class WordEmbedding:
         return st
 
     def _train_prepared(self, tokens: torch.Tensor, st: dict, compute_loss: bool, pipelined: bool = False) -> None:
+        tr = getattr(self, "trace", None)
+        if tr is not None:                 # benchmark tracing: K7 start / end events of every block
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._train_prepared_inner(tokens, st, compute_loss, pipelined)
+        if tr is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            tr.append((e0, e1))
+
+    def _train_prepared_inner(self, tokens: torch.Tensor, st: dict, compute_loss: bool, pipelined: bool) -> None:
         with monitor("WE_TRAIN_BLOCK", cuda=True):
             if st.get("dev"):
                 # pipelined: leave `side_ctas` SMs to the pull / push kernels running on the side stream
