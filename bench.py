@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--metric", default="words", choices=["words", "matrix_bw"],
                     help="words: WordEmbedding words/s (+ MatrixTable Get+Add GB/s as `secondary`); "
                          "matrix_bw: only the MatrixTable 1Mx512 Get+Add GB/s line (BASELINE.json config 2)")
+    ap.add_argument("--direct", action="store_true",
+                    help="world > 1: K7 trains in the row-sharded tables over NVLink (no block cache); not the default")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="world > 1: train / pull / push strictly one after the other (-is_pipeline 0)")
     return ap.parse_args()
@@ -201,6 +203,8 @@ def main():
     opt = WordEmbeddingOption(embeding_size=args.dim, window_size=args.window,
                               negative_num=args.negative, init_learning_rate=0.025, sample=0.0,
                               total_words=B * (K + W) * 2 * world, epoch=1)
+    if args.direct:
+        os.environ["MVB_WE_MODE"] = "direct"
     we = WordEmbedding(opt, args.vocab, seed=1)
 
     # synthetic corpus: a distinct block per step and per rank, staged in pinned host memory
@@ -219,7 +223,7 @@ def main():
     # world > 1: the reference's default pipeline (-is_pipeline 1): block i+1's PrepareData +
     # RequestParameter overlap block i's training, block i's AddDeltaParameter overlaps block i+1's.
     # Every step still issues exactly one prepare+pull, one train and one add-delta.
-    pipelined = world > 1 and not args.no_pipeline
+    pipelined = world > 1 and not args.no_pipeline and we.mode != "direct"
     blocks_list = [dev_blocks[i] for i in range(n_blocks)]        # stable tensor objects
 
     def step_device(i):

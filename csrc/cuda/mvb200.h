@@ -281,6 +281,13 @@ typedef struct MvbSgns {
   const float* scale_out;
   const int* neg_pool_size_ptr;  /* optional: pool size read on the DEVICE (mvb_we_prepare counts[2]);
                                     variant 20 only, overrides neg_pool_size                          */
+  /* direct mode (variant 20, nservers > 1): train IN the row-sharded tables over NVLink -- rows are loaded
+     from and reduced into their owners' shards (owner = id / rows_per_server, last server takes the
+     remainder) through the peer mappings; no block cache, no maps (Hogwild across GPUs)                 */
+  int nservers;
+  int64_t rows_per_server;
+  void* w_in_peers[MVB_MAX_RANKS];
+  void* w_out_peers[MVB_MAX_RANKS];
 } MvbSgns;
 int mvb_sgns_train(const MvbSgns* a, void* stream);
 int mvb_sgns_train_tma(const MvbSgns* a, void* stream);   /* TMA bulk-copy pipeline variant */

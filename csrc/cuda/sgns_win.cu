@@ -68,7 +68,20 @@ struct WinDev {
   int ko;            // 1 + negative
   int chunk;         // token positions per work unit (dynamic scheduling)
   unsigned int* ctr; // [0] next chunk, [1] CTAs that ran out of work (self-resetting)
+  // direct mode (Hogwild over NVLink): S > 0 => rows are addressed in the row-sharded tables themselves,
+  // owner = id / rps (last server takes the remainder), through the peer mappings of the shards
+  int S;
+  int64_t rps;
+  float* in_peer[MVB_MAX_RANKS];
+  float* out_peer[MVB_MAX_RANKS];
 };
+
+MVB_DEVINL float* row_of(float* const* peers, int S, int64_t rps, int64_t ld, float* local_base, int64_t rid) {
+  if (S <= 0) return local_base + rid * ld;
+  int64_t o = rid / rps;
+  if (o > S - 1) o = S - 1;
+  return peers[o] + (rid - o * rps) * ld;
+}
 
 // chunk tickets of the launch in flight (one K7 launch at a time per process; the last CTA resets them)
 __device__ unsigned int g_win_ctr[2];
@@ -318,7 +331,7 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
           const int tq = __ldg(a.tokens + q);
           if (tq >= 0) {
             const int rid = a.map_in ? __ldg(a.map_in + tq) : tq;
-            if (rid >= 0) iptr = a.w_in + (int64_t)rid * a.ld;
+            if (rid >= 0) iptr = row_of(a.in_peer, a.S, a.rps, a.ld, a.w_in, rid);
             if (a.scale_in) isc = __ldg(a.scale_in + tq);
           }
         }
@@ -394,7 +407,7 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
         float* optr = nullptr;
         if (lane < kKO && act) {
           const int r = b_rid[l * kKO + lane];
-          if (r >= 0) optr = a.w_out + (int64_t)r * a.ld;
+          if (r >= 0) optr = row_of(a.out_peer, a.S, a.rps, a.ld, a.w_out, r);
         }
         if (lane < kKO) {
           out_meta[st].ptr[lane] = optr;
@@ -644,7 +657,8 @@ extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream) {
   if (h->n_tokens <= 0) return 0;
   if (h->cbow || h->hs || h->use_adagrad || h->negative < 1 || h->negative > kKO - 1) return -20;
   if (h->dim % 4 || h->ld % 4 || h->dim > 512 || h->window < 1 || h->window > 15) return -21;
-  if ((reinterpret_cast<uintptr_t>(h->w_in) & 15) || (reinterpret_cast<uintptr_t>(h->w_out) & 15)) return -21;
+  if (h->nservers <= 1 &&
+      ((reinterpret_cast<uintptr_t>(h->w_in) & 15) || (reinterpret_cast<uintptr_t>(h->w_out) & 15))) return -21;
   WinDev a{};
   a.tokens = h->tokens; a.n_tokens = h->n_tokens; a.w_in = h->w_in; a.w_out = h->w_out;
   a.dim = h->dim; a.ld = h->ld; a.window = h->window; a.negative = h->negative; a.lr = h->lr;
@@ -653,6 +667,17 @@ extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream) {
   a.map_in = h->map_in;
   a.map_out = h->map_out; a.seed = h->seed; a.loss_sum = h->loss_sum; a.pair_count = h->pair_count;
   a.scale_in = h->scale_in; a.scale_out = h->scale_out;
+  a.S = 0;
+  if (h->nservers > 1) {
+    if (h->map_in || h->map_out || h->rows_per_server <= 0) return -21;
+    a.S = h->nservers;
+    a.rps = h->rows_per_server;
+    for (int s = 0; s < MVB_MAX_RANKS; ++s) {
+      a.in_peer[s] = s < h->nservers ? (float*)h->w_in_peers[s] : nullptr;
+      a.out_peer[s] = s < h->nservers ? (float*)h->w_out_peers[s] : nullptr;
+      if (s < h->nservers && (!a.in_peer[s] || !a.out_peer[s])) return -21;
+    }
+  }
   a.row_bytes = h->dim * 4;
   a.ko = 1 + h->negative;
   int dev = 0, max_smem = 0;

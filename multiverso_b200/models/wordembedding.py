@@ -158,8 +158,15 @@ class WordEmbedding:
         #                     stateful updaters need -- 3x the memory traffic for the plain-add updater)
         #   "bulk"            bulk-copy engine on `side_ctas` SMs reserved from K7's grid (op-rate bound:
         #                     ~27 M bulk ops/s per SM)
+        # world > 1 training mode: "block" (reference semantics: pull, train a block-local copy, push (new - old) / W)
+        # or "direct": K7 trains IN the row-sharded tables, loading rows from and reducing deltas into their owners'
+        # shards over NVLink (Hogwild across GPUs: no cache, no PrepareData, one kernel per block at any world size;
+        # link bound: ~20 KB per word cross NVLink instead of ~2 KB in block mode)
+        self.mode = os.environ.get("MVB_WE_MODE", "block")
         self.side_mode = os.environ.get("MVB_WE_SIDE_MODE", "lsu")
         self.side_ctas = int(os.environ.get("MVB_WE_SIDE_CTAS", "10" if self.side_mode == "bulk" else "1"))
+        if self.mode == "direct" and not (rt.size > 1 and self._dev_block_ok()):
+            self.mode = "block"
         if self.side_mode == "mbox" and rt.size > 1 and self._dev_block_ok() and self.input_table.S == rt.size:
             self.input_table.enable_row_mailbox()          # collective
             self.output_table.enable_row_mailbox()
@@ -193,6 +200,8 @@ class WordEmbedding:
         f = self.counts / self.counts.sum()
         q = np.power(self.counts, 0.75)
         q /= q.sum()
+        if getattr(self, "mode", "block") == "direct":
+            pos *= self.rt.size                    # every GPU's in-flight positions hit the same shared rows
         pairs = pos * (o.window_size + 1.0)
         g_in = pairs * f
         g_out = pairs * (f + o.negative_num * q)
@@ -212,7 +221,8 @@ class WordEmbedding:
 
     # ------------------------------------------------------------------ K7 launch
     def _launch(self, tokens: torch.Tensor, w_in, w_out, g2_in, g2_out, ld, map_in=None,
-                map_out=None, neg_pool=None, compute_loss=True, neg_pool_size_ptr=None, max_ctas=None) -> None:
+                map_out=None, neg_pool=None, compute_loss=True, neg_pool_size_ptr=None, max_ctas=None,
+                direct: bool = False) -> None:
         o = self.opt
         a = N.Sgns()
         a.tokens, a.n_tokens = tokens.data_ptr(), tokens.numel()
@@ -239,6 +249,12 @@ class WordEmbedding:
         a.pair_count = self.pairs.data_ptr()
         a.variant = self.kernel_variant
         a.max_ctas = self.max_ctas if max_ctas is None else max_ctas
+        if direct:
+            ti, to = self.input_table, self.output_table
+            a.nservers, a.rows_per_server = ti.S, ti.rps
+            for s_ in range(ti.S):
+                a.w_in_peers[s_], a.w_out_peers[s_] = ti.shard_ptrs[s_], to.shard_ptrs[s_]
+            a.variant = 20
         a.scale_in, a.scale_out = N.ptr(self.scale_in), N.ptr(self.scale_out)
         N.check(N.cuda_lib().mvb_sgns_train(C.byref(a), C.c_void_p(N.stream_ptr())), "mvb_sgns_train")
         self.kernel_launches += 1
@@ -263,6 +279,11 @@ class WordEmbedding:
                              None if self.g2_in is None else self.g2_in.shard,
                              None if self.g2_out is None else self.g2_out.shard, self.LD,
                              compute_loss=compute_loss)
+            return
+        if self.mode == "direct":
+            with monitor("WE_TRAIN_BLOCK", cuda=True):
+                self._launch(tokens, self.input_table.shard, self.output_table.shard, None, None, self.LD,
+                             compute_loss=compute_loss, direct=True)
             return
         if next_tokens is None and self._prefetched is None:
             st = self._prepare_block(tokens, wait=True)

@@ -313,6 +313,20 @@ def scenario_async():
     mv.barrier()
     emb = we.embeddings()
     check("wordembedding_pipelined", pl[-1] < pl[0] and all(l == l for l in pl) and bool(torch.isfinite(emb).all()), str(pl))
+    # direct mode: K7 trains in the row-sharded tables themselves over NVLink (bulk loads from / bulk reductions
+    # into peer shards), no block cache
+    os.environ["MVB_WE_MODE"] = "direct"
+    wd = WordEmbedding(WordEmbeddingOption(embeding_size=300, init_learning_rate=0.01), 200000)
+    os.environ.pop("MVB_WE_MODE")
+    dl = []
+    for it in range(5):
+        wd.loss.zero_(); wd.pairs.zero_()
+        wd.train_block(blocks[it % 3])
+        torch.cuda.synchronize()
+        dl.append(float(wd.loss.item()) / max(int(wd.pairs.item()), 1))
+    mv.barrier()
+    check("wordembedding_direct_mode", wd.mode == "direct" and dl[-1] < dl[0] and all(l == l for l in dl)
+          and bool(torch.isfinite(wd.embeddings()).all()), str(dl))
     mv.shutdown()
 
 
