@@ -190,6 +190,19 @@ __global__ void ftrl_update_kernel(float* z, float* n, const float* w, const flo
     n[i] = ni + gi * gi;
   }
 }
+// FTRL through the parameter server (FTRLObjective gradient, objective.cpp:260-336 + FTRLUpdater, updater.cpp:80-101):
+// the worker turns its averaged gradient into the pair (delta z, delta n) against the pulled n and w; the server
+// SUBTRACTS what it receives (sgd updater), so the negatives are emitted.
+__global__ void ftrl_delta_kernel(const float* __restrict__ n, const float* __restrict__ w, const float* __restrict__ g,
+                                  float* __restrict__ dz, float* __restrict__ dn, int64_t len, float alpha) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const float gi = g[i], ni = n[i];
+    const float sigma = (sqrtf(ni + gi * gi) - sqrtf(ni)) / alpha;
+    dz[i] = -(gi - sigma * w[i]);
+    dn[i] = -(gi * gi);
+  }
+}
 __global__ void regularize_kernel(float* grad, const float* w, int64_t len, int type, float coef) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
@@ -377,6 +390,15 @@ extern "C" int mvb_transpose_pad_f32(const float* in, int64_t rows, int64_t cols
 extern "C" int mvb_axpy_f32(float* y, const float* x, int64_t n, float alpha, void* stream) {
   if (n <= 0) return 0;
   axpy_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(y, x, n, alpha);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// (delta z, delta n) of an FTRL step, negated for a subtracting server (see ftrl_delta_kernel).
+extern "C" int mvb_ftrl_delta(const float* n, const float* w, const float* g, float* dz, float* dn, int64_t len,
+                              float alpha, void* stream) {
+  if (len <= 0) return 0;
+  ftrl_delta_kernel<<<ew_blocks(len), 256, 0, (cudaStream_t)stream>>>(n, w, g, dz, dn, len, alpha);
   MVB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -191,6 +191,8 @@ int mvb_stale_mark(uint8_t* stale /*[workers][rows]*/, int64_t rows, int nworker
                    const int64_t* row_ids, int64_t k /* k<0: all rows */, void* stream);
 int mvb_stale_take(uint8_t* stale_w /*[rows] for one worker*/, int64_t rows,
                    const int64_t* row_ids, int64_t k, uint8_t* out_mask, void* stream);
+/* ascending positions of the non-zero bytes of a mask; *count on the device */
+int mvb_mask_compact(const uint8_t* mask, int64_t n, int64_t* out_ids, int64_t* count, void* stream);
 
 /* ---- KV hash table (K5) ----------------------------------------------------- */
 /* open addressing, keys int64 (empty = INT64_MIN), values 8 bytes (f64 or i64) or 4
@@ -421,6 +423,9 @@ int mvb_ftrl_weights(const float* z, const float* n, float* w, int64_t len, floa
                      float l1, float l2, void* stream);
 int mvb_ftrl_update(float* z, float* n, const float* w, const float* g, int64_t len, float alpha,
                     void* stream);
+/* FTRL through the PS: dz = -(g - sigma w), dn = -g^2 with sigma = (sqrt(n + g^2) - sqrt(n)) / alpha */
+int mvb_ftrl_delta(const float* n, const float* w, const float* g, float* dz, float* dn, int64_t len,
+                   float alpha, void* stream);
 /* regulariser add: 1 = L1 sign(w)*c, 2 = L2 w*c */
 int mvb_regularize(float* grad, const float* w, int64_t len, int type, float coef, void* stream);
 

@@ -197,6 +197,28 @@ __global__ void stale_take_kernel(uint8_t* stale_w, int64_t rows, const int64_t*
   }
 }
 
+// ordered compaction of a byte mask into the list of set positions (one CTA: chunk per thread, block scan)
+__global__ void __launch_bounds__(1024)
+mask_compact_kernel(const uint8_t* __restrict__ mask, int64_t n, int64_t* __restrict__ out, int64_t* __restrict__ count) {
+  __shared__ int64_t part[1024];
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+  int64_t c = 0;
+  for (int64_t i = lo; i < hi; ++i) c += mask[i] != 0;
+  part[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int64_t t = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int64_t pos = part[threadIdx.x] - c;
+  for (int64_t i = lo; i < hi; ++i)
+    if (mask[i]) out[pos++] = i;
+  if (threadIdx.x == 1023) *count = part[1023];
+}
+
 RowMapDev to_dev(const MvbRowMap* m) {
   RowMapDev d{};
   d.num_row = m->num_row;
@@ -353,6 +375,14 @@ extern "C" int mvb_stale_take(uint8_t* stale_w, int64_t rows, const int64_t* row
   if (n <= 0) return 0;
   int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
   stale_take_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(stale_w, rows, row_ids, k, out_mask);
+  MVB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Positions of the non-zero bytes of mask[0..n), ascending; *count = how many (device).
+extern "C" int mvb_mask_compact(const uint8_t* mask, int64_t n, int64_t* out_ids, int64_t* count, void* stream) {
+  if (n <= 0) return 0;
+  mask_compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mask, n, out_ids, count);
   MVB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -12,7 +12,7 @@
 // model is pulled every sync_frequency minibatches (blocking, or double-buffered with `pipeline`).
 // The server updater is `sgd` unless -updater_type=... is given on the command line (adagrad /
 // momentum_sgd are applied by the owners inside the fused Add). FTRL is supported for the local
-// model; FTRL through the parameter server is available in the Python driver.
+// model and through the parameter server (two subtracting tables hold z and n).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -135,12 +135,18 @@ class DeviceModel {
     correct_ = static_cast<int*>(dev::DeviceAlloc(sizeof(int)));
     ResetStats();
     if (ftrl_) {
-      if (cfg.use_ps) Log::Fatal("logreg_gpu: FTRL through the parameter server is implemented in the Python driver "
-                                 "(python -m multiverso_b200.apps.logreg); use use_ps=false here\n");
       z_.Zero(n_w_);
       nacc_.Zero(n_w_);
     }
-    if (cfg.use_ps) {
+    if (cfg.use_ps && ftrl_) {
+      // FTRL through the parameter server (ps_model.cpp:38-67 FTRLTable): the servers hold z and n (two
+      // subtracting tables), the worker pulls both, derives w, pushes (delta z, delta n)
+      table_.reset(new dev::ArrayTable<float>(n_w_, dev::TableInit(), "sgd"));
+      table_n_.reset(new dev::ArrayTable<float>(n_w_, dev::TableInit(), "sgd"));
+      dz_.Zero(n_w_);
+      dn_.Zero(n_w_);
+      Pull(true);
+    } else if (cfg.use_ps) {
       table_.reset(new dev::ArrayTable<float>(n_w_));     // updater from -updater_type (sgd unless overridden)
       w_next_.Zero(n_w_);
       table_->Get(w_.get());
@@ -225,7 +231,13 @@ class DeviceModel {
 
   // Regularise, scale by the learning rate and update (local) or push (PS); lr schedule; periodic pull.
   void ApplyGradient() {
-    if (ftrl_) {
+    if (ftrl_ && table_) {
+      KERNEL_CHECK(mvb_ftrl_delta(nacc_.get(), w_.get(), grad_.get(), dz_.get(), dn_.get(), n_w_,
+                                  static_cast<float>(cfg_.alpha), nullptr));
+      table_->Wait(table_->AddAsync(dz_.get(), nullptr));
+      table_n_->Wait(table_n_->AddAsync(dn_.get(), nullptr));
+      launches_ += 3;
+    } else if (ftrl_) {
       KERNEL_CHECK(mvb_ftrl_update(z_.get(), nacc_.get(), w_.get(), grad_.get(), n_w_, static_cast<float>(cfg_.alpha), nullptr));
       ++launches_;
     } else {
@@ -258,6 +270,11 @@ class DeviceModel {
   // PullModel / GetPipelineTable (ps_model.cpp:205-271)
   void Pull(bool blocking) {
     if (!table_) return;
+    if (ftrl_) {                        // z and n live on the servers; w is derived lazily (Weights())
+      table_->Get(z_.get());
+      table_n_->Get(nacc_.get());
+      return;
+    }
     if (blocking) {
       if (pending_ >= 0) {
         table_->Wait(pending_);
@@ -300,6 +317,10 @@ class DeviceModel {
     fclose(f);
     if (!table_) {
       dev::CopyToDevice(w_.get(), host.data(), n_w_ * sizeof(float));
+      return;
+    }
+    if (ftrl_) {
+      Log::Error("init_model_file is ignored for FTRL through the parameter server (the servers hold z and n, not w)\n");
       return;
     }
     std::vector<float> cur(n_w_);
@@ -345,12 +366,13 @@ class DeviceModel {
   float lr_;
   int64_t updates_ = 0, launches_ = 0;
   int pending_ = -1;
-  DeviceBuffer<float> w_, w_next_, grad_, scaled_, z_, nacc_, err_, pred_, vals_, labels_, weights_, x_;
+  DeviceBuffer<float> w_, w_next_, grad_, scaled_, z_, nacc_, dz_, dn_, err_, pred_, vals_, labels_, weights_, x_;
   DeviceBuffer<int64_t> row_ptr_, keys_;
   std::vector<float> dense_host_;
   float* loss_ = nullptr;
   int* correct_ = nullptr;
   std::unique_ptr<dev::ArrayTable<float>> table_;
+  std::unique_ptr<dev::ArrayTable<float>> table_n_;    // FTRL through the PS: the n accumulators
 };
 
 double Test(const Configure& cfg, DeviceModel* model) {

@@ -652,6 +652,18 @@ struct MatrixTable<T>::Rows {
   // rows of its range once per worker, in worker order
   std::unique_ptr<SymmBuffer> stage_ids, stage_vals;
   int64_t stage_cap = 0;
+  // sparse delta pull: stale marks [slots x num_row], replicated on every rank (the adder marks every copy)
+  std::unique_ptr<SymmBuffer> stale;
+  int slots = 0;
+  uint8_t* mask = nullptr;        // device scratch [num_row]
+  int64_t* ids = nullptr;         // device scratch [num_row]
+  int64_t* count = nullptr;       // device scalar
+  void MarkStale(const int64_t* row_ids, int64_t k, int64_t num_row, CudaStream stream) {
+    if (!stale) return;
+    Context& c = Ctx();
+    for (int r = 0; r < c.size; ++r)
+      MVB_CHECK(mvb_stale_mark(static_cast<uint8_t*>(stale->peer(r)), num_row, slots, row_ids, k, stream));
+  }
 };
 
 template <typename T>
@@ -664,6 +676,59 @@ MatrixTable<T>::MatrixTable(int64_t num_row, int64_t num_col, const TableInit& i
   rows_->map.nservers = m.S;
   rows_->map.rows_per_server = m.rows_per_server;
   for (int s = 0; s < m.S; ++s) rows_->map.shard_ptrs[s] = m.shard_ptrs[s];
+}
+
+template <typename T>
+void MatrixTable<T>::EnableSparse(bool is_pipeline) {
+  if (rows_->stale) return;
+  Context& c = Ctx();
+  auto& m = TableAccess::Of<T>(*this);
+  rows_->slots = m.W * (is_pipeline ? 2 : 1);
+  const size_t bytes = static_cast<size_t>(rows_->slots) * static_cast<size_t>(this->num_row_);
+  rows_->stale.reset(new SymmBuffer(bytes));
+  std::vector<uint8_t> ones(bytes, 1);                      // everything is stale before the first pull
+  CopyToDevice(rows_->stale->local(), ones.data(), bytes);
+  rows_->mask = static_cast<uint8_t*>(DeviceAlloc(static_cast<size_t>(this->num_row_)));
+  rows_->ids = static_cast<int64_t*>(DeviceAlloc(static_cast<size_t>(this->num_row_) * sizeof(int64_t)));
+  rows_->count = static_cast<int64_t*>(DeviceAlloc(sizeof(int64_t)));
+  (void)c;
+  Barrier();
+}
+template <typename T>
+bool MatrixTable<T>::is_sparse() const { return static_cast<bool>(rows_->stale); }
+
+template <typename T>
+int64_t MatrixTable<T>::GetStale(int64_t* ids_out, T* rows_out, int slot, CudaStream stream) {
+  auto& m = TableAccess::Of<T>(*this);
+  const int64_t R = this->num_row_;
+  if (!rows_->stale) {
+    Log::Fatal("GetStale needs EnableSparse()\n");
+    return 0;
+  }
+  const int w = std::max(MV_WorkerId(), 0) + ((slot && rows_->slots > m.W) ? m.W : 0);
+  uint8_t* mine = static_cast<uint8_t*>(rows_->stale->local()) + static_cast<size_t>(w) * static_cast<size_t>(R);
+  MVB_CHECK(mvb_stale_take(mine, R, nullptr, -1, rows_->mask, stream));
+  MVB_CHECK(mvb_mask_compact(rows_->mask, R, ids_out, rows_->count, stream));
+  int64_t n = 0;
+  CopyToHost(&n, rows_->count, sizeof n, stream);           // synchronises the stream
+  if (n > 0) GetRows(ids_out, n, rows_out, 0, stream);
+  return n;
+}
+
+template <typename T>
+void MatrixTable<T>::AddSparse(const T* device_delta, const AddOption* option, CudaStream stream) {
+  if (rows_->stale) {
+    const int64_t R = this->num_row_, Ccols = this->num_col_;
+    MVB_CHECK(mvb_row_nonzero_mask(DType<T>::code, device_delta, R, Ccols, Ccols, rows_->mask, stream));
+    MVB_CHECK(mvb_mask_compact(rows_->mask, R, rows_->ids, rows_->count, stream));
+    int64_t n = 0;
+    CopyToHost(&n, rows_->count, sizeof n, stream);
+    this->Add(device_delta, option, stream);
+    if (n > 0) rows_->MarkStale(rows_->ids, n, R, stream);
+    StreamSync(stream);
+    return;
+  }
+  this->Add(device_delta, option, stream);
 }
 
 template <typename T>
@@ -684,6 +749,7 @@ int MatrixTable<T>::AddRowsAsync(const int64_t* ids, int64_t k, const T* vals, c
   if (m.upd->n_states == 0) {
     const float sign = m.upd->code == MVB_UPD_SGD ? -1.0f : 1.0f;
     MVB_CHECK(mvb_add_rows_red(DType<T>::code, &rows_->map, ids, k, vals, cols, sign, stream));
+    rows_->MarkStale(ids, k, this->num_row_, stream);
     return this->Record(stream);
   }
   void* st0 = m.state[0]->local();
@@ -692,6 +758,7 @@ int MatrixTable<T>::AddRowsAsync(const int64_t* ids, int64_t k, const T* vals, c
     const MvbAddOpt o = ToKernelOption(option, 0);
     MVB_CHECK(mvb_add_rows_owner(DType<T>::code, m.upd->code, m.shard->local(), st0, st1, m.row_lo[0], m.row_hi[0], cols,
                                  m.state_stride, ids, k, vals, cols, &o, stream));
+    rows_->MarkStale(ids, k, this->num_row_, stream);
     return this->Record(stream);
   }
   // collective: exchange the request sizes, publish the request in symmetric staging, owners apply
@@ -722,6 +789,7 @@ int MatrixTable<T>::AddRowsAsync(const int64_t* ids, int64_t k, const T* vals, c
                                    rows_->stage_vals->peer(r), cols, &o, stream));
     }
   }
+  if (k > 0) rows_->MarkStale(ids, k, this->num_row_, stream);
   Barrier(stream);
   return this->Record(stream);
 }
@@ -738,6 +806,7 @@ int MatrixTable<T>::AddRowsDeltaAsync(const int64_t* ids, int64_t k, const float
     Log::Fatal("AddRowsDelta needs an fp32 table with the default or sgd updater\n");
   const float sign = m.upd->code == MVB_UPD_SGD ? -1.0f : 1.0f;
   MVB_CHECK(mvb_add_rows_delta(&rows_->map, ids, k, cur, old, ld > 0 ? ld : this->num_col_, sign * scale, stream));
+  rows_->MarkStale(ids, k, this->num_row_, stream);
   return this->Record(stream);
 }
 

@@ -241,6 +241,62 @@ static void TestUpdaters() {
   }
 }
 
+// Sparse delta pull of the device MatrixTable (reference Matrix<T> with is_sparse, src/table/matrix.cpp:421-572):
+// the first GetStale returns every row, later ones exactly the rows somebody added to since this worker's last pull.
+static void TestSparseDeltaPull() {
+  const int W = MV_NumWorkers();
+  const int me = std::max(MV_WorkerId(), 0);
+  const int64_t rows = 1000, cols = 8;
+  dev::MatrixTable<float> table(rows, cols);
+  table.EnableSparse();
+  DeviceArray<int64_t> ids(rows);
+  DeviceArray<float> out(rows * cols);
+  EXPECT(table.GetStale(ids.ptr, out.ptr) == rows);           // everything is stale before the first pull
+  EXPECT(table.GetStale(ids.ptr, out.ptr) == 0);
+  dev::Barrier();
+  // worker w adds 1.0 to rows w, w + 2W, w + 4W, ... (row sets of different workers are disjoint)
+  std::vector<int64_t> mine;
+  for (int64_t r = me; r < rows; r += 2 * W) mine.push_back(r);
+  std::vector<float> vals(mine.size() * cols, 1.0f);
+  DeviceArray<int64_t> dids(mine.size());
+  DeviceArray<float> dvals(vals.size());
+  dids.Upload(mine);
+  dvals.Upload(vals);
+  table.AddRows(dids.ptr, static_cast<int64_t>(mine.size()), dvals.ptr);
+  dev::Barrier();
+  std::vector<int64_t> expect;
+  for (int64_t r = 0; r < rows; ++r)
+    if (r % (2 * W) < W) expect.push_back(r);
+  const int64_t n = table.GetStale(ids.ptr, out.ptr);
+  EXPECT(n == static_cast<int64_t>(expect.size()));
+  const std::vector<int64_t> got_ids = ids.Download();
+  const std::vector<float> got = out.Download();
+  bool ok = n == static_cast<int64_t>(expect.size());
+  for (int64_t i = 0; ok && i < n; ++i) ok = got_ids[i] == expect[i] && got[i * cols] == 1.0f && got[i * cols + cols - 1] == 1.0f;
+  EXPECT(ok);
+  EXPECT(table.GetStale(ids.ptr, out.ptr) == 0);
+  dev::Barrier();
+  // whole-table Add with two non-zero rows: only those become stale
+  std::vector<float> dense(rows * cols, 0.0f);
+  if (me == 0)
+    for (int64_t c = 0; c < cols; ++c) dense[5 * cols + c] = dense[999 * cols + c] = 2.0f;
+  DeviceArray<float> ddense(dense.size());
+  ddense.Upload(dense);
+  if (MV_CONFIG(sync) || dev::Size() == 1) {
+    table.AddSparse(ddense.ptr);
+  } else {
+    for (int r = 0; r < dev::Size(); ++r) {
+      if (dev::Rank() == r) table.AddSparse(ddense.ptr);
+      dev::Barrier();
+    }
+  }
+  dev::Barrier();
+  const int64_t n2 = table.GetStale(ids.ptr, out.ptr);
+  const std::vector<int64_t> ids2 = ids.Download();
+  EXPECT(n2 == 2 && ids2[0] == 5 && ids2[1] == 999);
+  dev::Barrier();
+}
+
 // The AddOption travels with each worker's request: per-worker learning rates under AdaGrad (per-worker
 // history).  Worker w adds delta = lr_w twice; the owner moves every element by rho/sqrt(1) + rho/sqrt(2) per
 // worker only if it divides worker w's delta by worker w's OWN learning rate.
@@ -355,6 +411,7 @@ int main(int argc, char* argv[]) {
   if (all || which == "aggregate") TestAggregate();
   if (all || which == "updaters") TestUpdaters();
   if (all || which == "peropt") TestPerWorkerOption();
+  if (all || which == "sparse") TestSparseDeltaPull();
   if (all || which == "checkpoint") TestCheckpoint();
   if (which == "bench") BenchMatrix(argc > 2 ? atoll(argv[2]) : 1000000);
   dev::Barrier();

@@ -200,6 +200,18 @@ class MatrixTable : public DenseTable<T> {
   int AddRowsDeltaAsync(const int64_t* device_row_ids, int64_t k, const float* device_cur, const float* device_old,
                         int64_t ld, float scale, CudaStream stream = nullptr);
 
+  // Sparse delta pull (the reference's Matrix<T> with is_sparse, src/table/matrix.cpp:421-572): after
+  // EnableSparse (collective) every Add marks the rows it touches stale for every worker -- a whole-table Add
+  // only its non-zero rows (matrix.cpp:151-164) -- and GetStale returns just the rows that changed since this
+  // worker's previous GetStale: their ids (ascending, device_ids_out[num_row]) and values
+  // (device_rows_out[count x num_col]); the first call returns every row.  `is_pipeline` keeps a second set of
+  // marks per worker (`slot` 1) for double-buffered clients.
+  void EnableSparse(bool is_pipeline = false);
+  bool is_sparse() const;
+  int64_t GetStale(int64_t* device_ids_out, T* device_rows_out, int slot = 0, CudaStream stream = nullptr);
+  // whole-table Add that honours the sparse bookkeeping (DenseTable::Add does not know about it)
+  void AddSparse(const T* device_delta, const AddOption* option = nullptr, CudaStream stream = nullptr);
+
  private:
   struct Rows;
   std::shared_ptr<Rows> rows_;

@@ -301,11 +301,16 @@ class LogRegModel:
                                             C.c_int64(self.n_w), C.c_float(cfg.alpha), st))
                 self.kernel_launches += 1
             else:
-                # FTRLObjective emits (dz, dn); the server subtracts, so push the negatives
-                g = self.grad
-                sigma = (torch.sqrt(self.nacc + g * g) - torch.sqrt(self.nacc)) / cfg.alpha
-                self.table.add_async(-(g - sigma * self.w))
-                self.table_n.add_async(-(g * g))
+                # FTRLObjective emits (dz, dn); the server subtracts, so the kernel emits the negatives
+                if getattr(self, "_dz", None) is None:
+                    self._dz, self._dn = torch.empty_like(self.grad), torch.empty_like(self.grad)
+                N.check(lib.mvb_ftrl_delta(C.c_void_p(self.nacc.data_ptr()), C.c_void_p(self.w.data_ptr()),
+                                           C.c_void_p(self.grad.data_ptr()), C.c_void_p(self._dz.data_ptr()),
+                                           C.c_void_p(self._dn.data_ptr()), C.c_int64(self.n_w), C.c_float(cfg.alpha), st),
+                        "mvb_ftrl_delta")
+                self.kernel_launches += 1
+                self.table.add_async(self._dz)
+                self.table_n.add_async(self._dn)
         else:
             scaled = self.grad * self.lr if cfg.updater_type in ("sgd", "default") else self.grad
             if self.table is None:

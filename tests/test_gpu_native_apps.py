@@ -148,3 +148,35 @@ def test_device_checkpoint_roundtrip_with_state(mv_device, tmp_path, updater):
     assert mv.load_table(b, path)
     b.add(d2, opt)
     assert torch.allclose(b.get(), expect, rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,use_ps", [(1, "false"), (1, "true"), (2, "true")])
+def test_logreg_gpu_binary_ftrl(tmp_path, n, use_ps):
+    """FTRL in the native GPU application, locally and THROUGH the parameter server (ps_model.cpp:38-67 FTRLTable:
+    the servers hold z and n, workers push (delta z, delta n))."""
+    if n not in _ranks():
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(2)
+    D, Ns = 2000, 6000
+    wtrue = rng.normal(size=D)
+    X = np.zeros((Ns, D), np.float32)
+    for i in range(Ns):
+        X[i, rng.choice(D, size=20, replace=False)] = 1.0
+    y = (X @ wtrue > 0).astype(np.int64)
+    for name, lo, hi in (("tr", 0, 5000), ("te", 5000, 6000)):
+        with open(tmp_path / f"{name}.svm", "w") as f:
+            for xi, yi in zip(X[lo:hi], y[lo:hi]):
+                nz = np.nonzero(xi)[0]
+                f.write(f"{int(yi)} " + " ".join(f"{k}:{xi[k]:.0f}" for k in nz) + "\n")
+    cfg = tmp_path / "ftrl.config"
+    cfg.write_text(f"input_size={D}\noutput_size=1\nsparse=true\nobjective_type=ftrl\nupdater_type=ftrl\n"
+                   f"train_epoch=4\nminibatch_size=20\nlearning_rate=0.5\ntrain_file={tmp_path}/tr.svm\n"
+                   f"test_file={tmp_path}/te.svm\noutput_file=\noutput_model_file=\nuse_ps={use_ps}\n"
+                   f"alpha=0.1\nbeta=1\nlambda1=0.01\nlambda2=0\nregular_type=default\nsync_frequency=1\n")
+    r = subprocess.run(_launcher(n) + [os.path.join(BIN, "logreg_gpu"), str(cfg)], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = _json_lines(r.stdout)
+    assert len(res) == n
+    for x in res:
+        assert x["test_error"] < 0.4 and x["kernel_launches"] > 0, x
