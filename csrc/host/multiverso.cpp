@@ -57,10 +57,14 @@ bool MV_SaveTable(int table_id, const std::string& uri) {
   auto& tables = table_factory::ServerTables();
   bool ok = true;
   if (MV_ServerId() >= 0) {
-    if (table_id < 0 || table_id >= static_cast<int>(tables.size())) return false;
-    std::unique_ptr<Stream> s(StreamFactory::GetStream(URI(ShardUri(uri)), FileOpenMode::BinaryWrite));
-    ok = s && s->Good();
-    if (ok) tables[table_id]->Store(s.get());
+    // decide first, ALWAYS reach the barrier: worker-only ranks are already waiting in it
+    ok = table_id >= 0 && table_id < static_cast<int>(tables.size());
+    if (ok) {
+      std::unique_ptr<Stream> s(StreamFactory::GetStream(URI(ShardUri(uri)), FileOpenMode::BinaryWrite));
+      ok = s && s->Good();
+      if (ok) tables[table_id]->Store(s.get());
+      ok = ok && s->Good();
+    }
   }
   MV_Barrier();
   return ok;
@@ -70,10 +74,13 @@ bool MV_LoadTable(int table_id, const std::string& uri) {
   auto& tables = table_factory::ServerTables();
   bool ok = true;
   if (MV_ServerId() >= 0) {
-    if (table_id < 0 || table_id >= static_cast<int>(tables.size())) return false;
-    std::unique_ptr<Stream> s(StreamFactory::GetStream(URI(ShardUri(uri)), FileOpenMode::BinaryRead));
-    ok = s && s->Good();
-    if (ok) tables[table_id]->Load(s.get());
+    ok = table_id >= 0 && table_id < static_cast<int>(tables.size());
+    if (ok) {
+      std::unique_ptr<Stream> s(StreamFactory::GetStream(URI(ShardUri(uri)), FileOpenMode::BinaryRead));
+      ok = s && s->Good();
+      if (ok) tables[table_id]->Load(s.get());
+      ok = ok && s->Good() && !s->Failed();   // tables mark the stream when the checkpoint is truncated
+    }
   }
   MV_Barrier();
   return ok;

@@ -29,7 +29,7 @@ MV_DEFINE_int(port, 55555, "base port of the TCP control plane");
 namespace {
 
 struct FrameHeader {
-  uint32_t kind;   // 0 = Message, 1 = raw
+  uint32_t kind;   // 0 = Message, 1 = raw, 2 = bye (the peer is shutting down in order)
   uint32_t src;
   uint64_t len;
 };
@@ -253,7 +253,10 @@ void TcpNet::EstablishMesh(const std::vector<std::string>& eps) {
 
 void TcpNet::Finalize() {
   if (!active_) return;
-  stopping_ = true;
+  stopping_ = true;     // from here on a failed send is not an error (the peer may have closed already)
+  // tell every peer that this end closes on purpose: an EOF without a preceding bye is a dead rank
+  for (int i = 0; i < size_; ++i)
+    if (i != rank_ && fds_[i] >= 0) WriteFrame(i, 2, {});
   for (int fd : fds_)
     if (fd >= 0) ::shutdown(fd, SHUT_RDWR);
   if (receiver_.joinable()) receiver_.join();
@@ -277,6 +280,7 @@ void TcpNet::ReceiverLoop() {
       owner.push_back(i);
     }
   size_t open = pfds.size();
+  std::vector<char> said_bye(pfds.size(), 0);
   while (!stopping_ && open > 0) {
     int rc = ::poll(pfds.data(), pfds.size(), 200);
     if (rc <= 0) continue;
@@ -284,8 +288,17 @@ void TcpNet::ReceiverLoop() {
       if (pfds[k].fd < 0 || !(pfds[k].revents & (POLLIN | POLLHUP | POLLERR))) continue;
       FrameHeader h;
       if (!ReadExact(pfds[k].fd, &h, sizeof h)) {
+        // an orderly shutdown closes sockets only after stopping_ is set; a peer that disappears before that is
+        // dead, and every request it still owes a reply to would wait forever: say so once, loudly
+        if (!stopping_ && !said_bye[k])
+          Log::Error("rank %d: lost the connection to rank %d (peer exited or crashed); requests to it cannot complete\n",
+                     rank_, owner[k]);
         pfds[k].fd = -1;
         --open;
+        continue;
+      }
+      if (h.kind == 2) {
+        said_bye[k] = 1;
         continue;
       }
       if (h.kind == 0) {

@@ -358,9 +358,21 @@ void MatrixServerTable<T>::Store(Stream* s) {
 }
 template <typename T>
 void MatrixServerTable<T>::Load(Stream* s) {
-  s->Read(storage_.data(), storage_.size() * sizeof(T));
+  // a truncated checkpoint must not leave the shard half loaded and report success: read into a scratch
+  // buffer, install only a complete shard (reference: raw dump, no length check, array_table.cpp:147-151)
+  std::vector<T> shard(storage_.size());
+  const size_t want = shard.size() * sizeof(T);
+  if (s->Read(shard.data(), want) != want) {
+    Log::Error("table checkpoint is shorter than the shard (%zu bytes expected): not loaded\n", want);
+    s->MarkFailed();
+    return;
+  }
+  std::copy(shard.begin(), shard.end(), storage_.begin());
   std::vector<char> st(updater_->StateBytes());
-  if (!st.empty() && s->Read(st.data(), st.size()) == st.size()) updater_->LoadState(st.data());
+  if (!st.empty()) {
+    if (s->Read(st.data(), st.size()) == st.size()) updater_->LoadState(st.data());
+    else Log::Info("table checkpoint carries no updater state (reference-format file): state left as is\n");
+  }
 }
 
 template class MatrixWorkerTable<float>;

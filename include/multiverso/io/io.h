@@ -28,6 +28,12 @@ class Stream {
   virtual size_t Read(void* buf, size_t size) = 0;
   virtual bool Good() = 0;
   virtual void Flush() {}
+  // set by a reader that found the content incomplete (e.g. a truncated table checkpoint)
+  void MarkFailed() { failed_ = true; }
+  bool Failed() const { return failed_; }
+
+ private:
+  bool failed_ = false;
 };
 
 class StreamFactory {
