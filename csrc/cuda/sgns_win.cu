@@ -11,13 +11,14 @@
 // position and shared by its contexts, scores are a [contexts x D]·[D x (1+K)] tile evaluated on
 // pre-update rows):
 //
-//   producer warp   walks the CTA's contiguous token range in order.  Per position: ONE cp.async.bulk
-//                   of the input row into a CTA-wide ring (every row is a context of up to 2W centres,
-//                   so it crosses L2 once instead of ~6 times) and 1+K cp.async.bulk of the centre /
-//                   negative output rows into the owning consumer's double-buffered stage.  Negative
-//                   sampling (hash RNG -> alias table or block pool) and the id -> cache-slot maps are
-//                   evaluated 32 positions at a time, one lane per position, so their dependent loads
-//                   are paid once per batch.
+//   producer warps walk the CTA's contiguous token range in order, as two independent streams.  Warp 0,
+//                   per position: ONE cp.async.bulk of the input row into a CTA-wide ring (every row is
+//                   a context of up to 2W centres, so it crosses L2 once instead of ~6 times); one lane
+//                   per position waits for its slot and issues its copy.  Warp 1, per position: 1+K
+//                   cp.async.bulk of the centre / negative output rows into the owning consumer's
+//                   double-buffered stage.  Negative sampling (hash RNG -> alias table or block pool)
+//                   and the id -> cache-slot maps are evaluated 32 positions at a time, one lane per
+//                   position, so their dependent loads are paid once per batch.
 //   consumer warps  position p -> warp (p mod NW).  Phase 1 (output rows in registers): per context
 //                   1+K dots, sigmoid / error terms, the context's input delta sum_k g_k·out_k goes
 //                   through a small staging ring and leaves with ONE cp.reduce.async.bulk.add.f32.
@@ -35,7 +36,7 @@
 namespace {
 
 constexpr int kNW = 10;            // consumer warps per CTA
-constexpr int kThreads = 32 * (1 + kNW);
+constexpr int kThreads = 32 * (2 + kNW);   // two producer warps + the consumers
 constexpr int kKO = 8;             // max output rows per position (centre + up to 7 negatives)
 constexpr int kDinSlots = 3;       // per-warp staging ring of input-row deltas
 constexpr int kRelLanes = 8;       // lanes that issue row reductions / arrive on out_empty
@@ -66,8 +67,7 @@ struct WinDev {
   int ring;          // input-row ring slots (>= 2*kNW + 2*window + 1)
   int nw;            // active consumer warps (<= kNW)
   int ko;            // 1 + negative
-  int chunk;         // token positions per work unit (dynamic scheduling)
-  unsigned int* ctr; // [0] next chunk, [1] CTAs that ran out of work (self-resetting)
+  int chunk;         // token positions per work unit (chunk c belongs to CTA c mod gridDim.x)
   // direct mode (Hogwild over NVLink): S > 0 => rows are addressed in the row-sharded tables themselves,
   // owner = id / rps (last server takes the remainder), through the peer mappings of the shards
   int S;
@@ -83,8 +83,6 @@ MVB_DEVINL float* row_of(float* const* peers, int S, int64_t rps, int64_t ld, fl
   return peers[o] + (rid - o * rps) * ld;
 }
 
-// chunk tickets of the launch in flight (one K7 launch at a time per process; the last CTA resets them)
-__device__ unsigned int g_win_ctr[2];
 
 struct OutMeta {
   float* ptr[kKO];   // global row addresses (nullptr = row unused)
@@ -281,8 +279,8 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
   const int R = a.ring;
   const int NW = a.nw;
 
-  // Work units are chunks of `a.chunk` consecutive token positions handed out by an atomic counter (a CTA
-  // slowed down by co-resident row pull / push kernels simply takes fewer).  Inside a CTA the chunks form ONE
+  // Work units are chunks of `a.chunk` consecutive token positions, chunk c on CTA c mod gridDim.x (one chunk
+  // per CTA unless MVB_WIN_CHUNK says otherwise).  Inside a CTA the chunks form ONE
   // stream of virtual positions G = 0, 1, 2, ...: chunk [ra, rb) contributes rb - ra + 4W of them (local index
   // i <-> centre token ra - 2W + i, ring entry i <-> input token ra - W + i, empty beyond the chunk), so ring
   // slots, stages and barrier phases simply continue across chunks.
@@ -301,160 +299,172 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
   }
   __syncthreads();
 
-  if (warp == 0) {
-    // ================================ PRODUCER =========================================
+  if (warp < 2) {
+    // ================================ PRODUCERS ========================================
+    // Two warps, two independent streams over the same virtual positions: warp 0 feeds the input-row ring,
+    // warp 1 samples the negatives and feeds the output stages.  (One warp doing both was the bottleneck of
+    // the kernel: the consumers spent half of their samples waiting in out_full while the producer never
+    // waited on anything.)
     float** b_inptr = reinterpret_cast<float**>(smem + L.batch);
     int* b_rid = reinterpret_cast<int*>(smem + L.batch + 32 * 8);
     int* b_act = b_rid + 32 * kKO;
-    const int pool_n = a.neg_pool_size_ptr ? __ldg(a.neg_pool_size_ptr) : a.neg_pool_size;
     float* b_isc = reinterpret_cast<float*>(b_act + 32);
     float* b_osc = b_isc + 32;
+    const int pool_n = (warp == 1 && a.neg_pool_size_ptr) ? __ldg(a.neg_pool_size_ptr) : a.neg_pool_size;
     int64_t G0 = 0;                          // virtual positions emitted by earlier chunks
-    for (;;) {
-    long long c = 0;
-    if (lane == 0) c = (long long)atomicAdd(a.ctr, 1u);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (c >= n_chunks) break;
-    const int64_t ra = c * (int64_t)a.chunk;
-    const int64_t rb = (ra + a.chunk < a.n_tokens) ? ra + a.chunk : a.n_tokens;
-    const int64_t len = rb - ra;
-    const int64_t nj = len + 2 * W;          // ring entries with a token behind them
-    const int64_t nv = len + 4 * W;          // virtual centres of this chunk
-    for (int64_t i0 = 0; i0 < nv; i0 += 32) {
-      {
-        const int64_t i = i0 + lane;
-        // input row of ring position j = i
-        const int64_t q = ra - W + i;
-        float* iptr = nullptr;
-        float isc = 1.f;
-        if (i < nj && q >= 0 && q < a.n_tokens) {
-          const int tq = __ldg(a.tokens + q);
-          if (tq >= 0) {
-            const int rid = a.map_in ? __ldg(a.map_in + tq) : tq;
-            if (rid >= 0) iptr = row_of(a.in_peer, a.S, a.rps, a.ld, a.w_in, rid);
-            if (a.scale_in) isc = __ldg(a.scale_in + tq);
-          }
-        }
-        b_inptr[lane] = iptr;
-        b_isc[lane] = isc;
-        // centre + negatives of virtual centre i
-        const int64_t p = ra - 2 * W + i;
-        int tp = -1;
-        if (i >= 2 * W && i < 2 * W + len) tp = __ldg(a.tokens + p);
-        int rid[kKO];
-        float osc[kKO];
-#pragma unroll
-        for (int k = 0; k < kKO; ++k) { rid[k] = -1; osc[k] = 1.f; }
-        if (tp >= 0) {
-          const uint64_t prng = hash64(a.seed ^ (uint64_t)(p + 1) * 0x9E3779B97F4A7C15ull);
-          int t[kKO];
-#pragma unroll
-          for (int k = 1; k < kKO; ++k) {
-            t[k] = -1;
-            if (k < a.ko) {
-              const uint64_t r = hash64(prng ^ ((uint64_t)k * 0xD6E8FEB86659FD93ull));
-              if (a.neg_pool) {
-                t[k] = pool_n > 0 ? __ldg(a.neg_pool + (r >> 8) % (uint64_t)pool_n) : -1;
-              } else {
-                const uint32_t idx = (uint32_t)((r >> 32) % (uint64_t)a.vocab);
-                const float u = (float)(r & 0xFFFFFF) * (1.0f / 16777216.0f);
-                t[k] = (u < __ldg(a.alias_prob + idx)) ? (int)idx : __ldg(a.alias_idx + idx);
-              }
-              if (t[k] == tp) t[k] = -1;                 // Parse(): target == word_idx is skipped
-            }
-          }
-          rid[0] = a.map_out ? __ldg(a.map_out + tp) : tp;
-          if (a.scale_out) osc[0] = __ldg(a.scale_out + tp);
-#pragma unroll
-          for (int k = 1; k < kKO; ++k)
-            if (t[k] >= 0) {
-              rid[k] = a.map_out ? __ldg(a.map_out + t[k]) : t[k];
-              if (a.scale_out) osc[k] = __ldg(a.scale_out + t[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kKO; ++k) { b_rid[lane * kKO + k] = rid[k]; b_osc[lane * kKO + k] = osc[k]; }
-        b_act[lane] = (tp >= 0 && rid[0] >= 0) ? 1 : 0;
-      }
-      __syncwarp();
-      const int nb = (int)((nv - i0) < 32 ? (nv - i0) : 32);
-      for (int l = 0; l < nb; ++l) {
-        const int64_t ii = G0 + i0 + l;                 // position in the CTA's virtual stream
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+      const int64_t ra = c * (int64_t)a.chunk;
+      const int64_t rb = (ra + a.chunk < a.n_tokens) ? ra + a.chunk : a.n_tokens;
+      const int64_t len = rb - ra;
+      const int64_t nj = len + 2 * W;          // ring entries with a token behind them
+      const int64_t nv = len + 4 * W;          // virtual centres of this chunk
+      if (warp == 0) {
         // ---- input-row ring: every virtual position owns an entry (empty beyond the chunk) -----
-        if (lane == 0) {
-          const int slot = (int)(ii % R);
-          const uint32_t round = (uint32_t)(ii / R);
-          mbar_wait(in_empty + slot, (round & 1u) ^ 1u);
-          // a row nobody needed (shrunk window, break) can be released before its copy landed:
-          // never re-arm a slot whose previous transaction is still in flight
-          if (round > 0) mbar_wait(in_full + slot, (round - 1u) & 1u);
-          float* ptr = (i0 + l < nj) ? b_inptr[l] : nullptr;
-          in_ptr[slot] = ptr;
-          in_scale[slot] = b_isc[l];
-          if (ptr) {
-            mbar_arrive_expect_tx(in_full + slot, (uint32_t)a.row_bytes);
-            bulk_g2s(in_rows + (size_t)slot * a.row_bytes, ptr, (uint32_t)a.row_bytes, in_full + slot);
-          } else {
-            mbar_arrive(in_full + slot);
+        for (int64_t i0 = 0; i0 < nv; i0 += 32) {
+          {
+            const int64_t i = i0 + lane;
+            const int64_t q = ra - W + i;
+            float* iptr = nullptr;
+            float isc = 1.f;
+            if (i < nj && q >= 0 && q < a.n_tokens) {
+              const int tq = __ldg(a.tokens + q);
+              if (tq >= 0) {
+                const int rid = a.map_in ? __ldg(a.map_in + tq) : tq;
+                if (rid >= 0) iptr = row_of(a.in_peer, a.S, a.rps, a.ld, a.w_in, rid);
+                if (a.scale_in) isc = __ldg(a.scale_in + tq);
+              }
+            }
+            b_inptr[lane] = iptr;
+            b_isc[lane] = isc;
           }
+          __syncwarp();
+          const int nb = (int)((nv - i0) < 32 ? (nv - i0) : 32);
+          // one lane per position: each waits for ITS slot and issues ITS copy (slots of a batch are distinct
+          // because R >= 32 is not guaranteed -> walk the batch in groups of at most R lanes)
+          for (int l0 = 0; l0 < nb; l0 += R) {
+            const int l = l0 + lane;
+            if (lane < R && l < nb) {
+              const int64_t ii = G0 + i0 + l;
+              const int slot = (int)(ii % R);
+              const uint32_t round = (uint32_t)(ii / R);
+              mbar_wait(in_empty + slot, (round & 1u) ^ 1u);
+              // a row nobody needed (shrunk window, break) can be released before its copy landed:
+              // never re-arm a slot whose previous transaction is still in flight
+              if (round > 0) mbar_wait(in_full + slot, (round - 1u) & 1u);
+              float* ptr = (i0 + l < nj) ? b_inptr[l] : nullptr;
+              in_ptr[slot] = ptr;
+              in_scale[slot] = b_isc[l];
+              if (ptr) {
+                mbar_arrive_expect_tx(in_full + slot, (uint32_t)a.row_bytes);
+                bulk_g2s(in_rows + (size_t)slot * a.row_bytes, ptr, (uint32_t)a.row_bytes, in_full + slot);
+              } else {
+                mbar_arrive(in_full + slot);
+              }
+            }
+            __syncwarp();
+          }
+          __syncwarp();       // batch scratch is re-written next round
         }
-        // ---- output stage of the owning consumer -----------------------------------------
+      } else {
+        // ---- centre + negatives of every virtual centre, into the stage of the owning consumer ----
+        for (int64_t i0 = 0; i0 < nv; i0 += 32) {
+          {
+            const int64_t i = i0 + lane;
+            const int64_t p = ra - 2 * W + i;
+            int tp = -1;
+            if (i >= 2 * W && i < 2 * W + len) tp = __ldg(a.tokens + p);
+            int rid[kKO];
+            float osc[kKO];
+#pragma unroll
+            for (int k = 0; k < kKO; ++k) { rid[k] = -1; osc[k] = 1.f; }
+            if (tp >= 0) {
+              const uint64_t prng = hash64(a.seed ^ (uint64_t)(p + 1) * 0x9E3779B97F4A7C15ull);
+              int t[kKO];
+#pragma unroll
+              for (int k = 1; k < kKO; ++k) {
+                t[k] = -1;
+                if (k < a.ko) {
+                  const uint64_t r = hash64(prng ^ ((uint64_t)k * 0xD6E8FEB86659FD93ull));
+                  if (a.neg_pool) {
+                    t[k] = pool_n > 0 ? __ldg(a.neg_pool + (r >> 8) % (uint64_t)pool_n) : -1;
+                  } else {
+                    const uint32_t idx = (uint32_t)((r >> 32) % (uint64_t)a.vocab);
+                    const float u = (float)(r & 0xFFFFFF) * (1.0f / 16777216.0f);
+                    t[k] = (u < __ldg(a.alias_prob + idx)) ? (int)idx : __ldg(a.alias_idx + idx);
+                  }
+                  if (t[k] == tp) t[k] = -1;                 // Parse(): target == word_idx is skipped
+                }
+              }
+              rid[0] = a.map_out ? __ldg(a.map_out + tp) : tp;
+              if (a.scale_out) osc[0] = __ldg(a.scale_out + tp);
+#pragma unroll
+              for (int k = 1; k < kKO; ++k)
+                if (t[k] >= 0) {
+                  rid[k] = a.map_out ? __ldg(a.map_out + t[k]) : t[k];
+                  if (a.scale_out) osc[k] = __ldg(a.scale_out + t[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kKO; ++k) { b_rid[lane * kKO + k] = rid[k]; b_osc[lane * kKO + k] = osc[k]; }
+            b_act[lane] = (tp >= 0 && rid[0] >= 0) ? 1 : 0;
+          }
+          __syncwarp();
+          const int nb = (int)((nv - i0) < 32 ? (nv - i0) : 32);
+          for (int l = 0; l < nb; ++l) {
+            const int64_t ii = G0 + i0 + l;                 // position in the CTA's virtual stream
+            const int cw = (int)(ii % NW);
+            const int64_t n = ii / NW;
+            const int st = cw * 2 + (int)(n & 1);
+            mbar_wait(out_empty + st, (uint32_t)((n >> 1) & 1) ^ 1u);
+            const int act = b_act[l];
+            float* optr = nullptr;
+            if (lane < kKO && act) {
+              const int r = b_rid[l * kKO + lane];
+              if (r >= 0) optr = row_of(a.out_peer, a.S, a.rps, a.ld, a.w_out, r);
+            }
+            if (lane < kKO) {
+              out_meta[st].ptr[lane] = optr;
+              out_meta[st].scale[lane] = b_osc[l * kKO + lane];
+            }
+            if (lane == 0) {
+              out_meta[st].active = act;
+              out_meta[st].p = (long long)(ra - 2 * W + i0 + l);
+            }
+            const uint32_t have = __ballot_sync(0xffffffffu, optr != nullptr);
+            __syncwarp();     // every lane's meta pointer is written before the release-arrive
+            if (lane == 0) {
+              if (have) mbar_arrive_expect_tx(out_full + st, (uint32_t)__popc(have) * (uint32_t)a.row_bytes);
+              else mbar_arrive(out_full + st);
+            }
+            __syncwarp();     // expect_tx is armed before any copy can complete_tx
+            if (optr)
+              bulk_g2s(out_rows + ((size_t)st * a.ko + lane) * a.row_bytes, optr, (uint32_t)a.row_bytes,
+                       out_full + st);
+          }
+          __syncwarp();       // batch scratch is re-written next round
+        }
+      }
+      G0 += nv;
+    }
+    if (warp == 1) {
+      // out of work: one end marker per consumer warp (in stream order)
+      for (int k = 0; k < NW; ++k) {
+        const int64_t ii = G0 + k;
         const int cw = (int)(ii % NW);
         const int64_t n = ii / NW;
         const int st = cw * 2 + (int)(n & 1);
-        mbar_wait(out_empty + st, (uint32_t)((n >> 1) & 1) ^ 1u);
-        const int act = b_act[l];
-        float* optr = nullptr;
-        if (lane < kKO && act) {
-          const int r = b_rid[l * kKO + lane];
-          if (r >= 0) optr = row_of(a.out_peer, a.S, a.rps, a.ld, a.w_out, r);
-        }
-        if (lane < kKO) {
-          out_meta[st].ptr[lane] = optr;
-          out_meta[st].scale[lane] = b_osc[l * kKO + lane];
-        }
         if (lane == 0) {
-          out_meta[st].active = act;
-          out_meta[st].p = (long long)(ra - 2 * W + i0 + l);
+          mbar_wait(out_empty + st, (uint32_t)((n >> 1) & 1) ^ 1u);
+          out_meta[st].active = -1;
+          mbar_arrive(out_full + st);
         }
-        const uint32_t have = __ballot_sync(0xffffffffu, optr != nullptr);
-        __syncwarp();     // every lane's meta pointer is written before the release-arrive
-        if (lane == 0) {
-          if (have) mbar_arrive_expect_tx(out_full + st, (uint32_t)__popc(have) * (uint32_t)a.row_bytes);
-          else mbar_arrive(out_full + st);
-        }
-        __syncwarp();     // expect_tx is armed before any copy can complete_tx
-        if (optr)
-          bulk_g2s(out_rows + ((size_t)st * a.ko + lane) * a.row_bytes, optr, (uint32_t)a.row_bytes,
-                   out_full + st);
-      }
-      __syncwarp();       // batch scratch is re-written next round
-    }
-    G0 += nv;
-    }
-    // out of work: one end marker per consumer warp (in stream order), then retire the counters
-    for (int k = 0; k < NW; ++k) {
-      const int64_t ii = G0 + k;
-      const int cw = (int)(ii % NW);
-      const int64_t n = ii / NW;
-      const int st = cw * 2 + (int)(n & 1);
-      if (lane == 0) {
-        mbar_wait(out_empty + st, (uint32_t)((n >> 1) & 1) ^ 1u);
-        out_meta[st].active = -1;
-        mbar_arrive(out_full + st);
-      }
-    }
-    if (lane == 0) {
-      if (atomicAdd(a.ctr + 1, 1u) == gridDim.x - 1) {   // every CTA has drawn its last ticket
-        a.ctr[0] = 0u;
-        a.ctr[1] = 0u;
       }
     }
     return;
   }
 
   // ================================ CONSUMERS =========================================
-  const int cw = warp - 1;
+  const int cw = warp - 2;
   if (cw >= NW) return;
   const int nvec = a.dim >> 2;
   unsigned char* my_din = din_rows + (size_t)cw * kDinSlots * a.row_bytes;
@@ -701,9 +711,6 @@ extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream) {
     }
   }
   a.nw = nw;
-  void* ctr = nullptr;
-  MVB_CUDA_CHECK(cudaGetSymbolAddress(&ctr, g_win_ctr));
-  a.ctr = reinterpret_cast<unsigned int*>(ctr);
   int blocks = mvb_num_sms();
   if (h->max_ctas > 0 && h->max_ctas < blocks) blocks = h->max_ctas;
   // tiny inputs use fewer CTAs (>= 64 positions each)
@@ -711,8 +718,8 @@ extern "C" int mvb_sgns_train_win(const MvbSgns* h, void* stream) {
   if ((int64_t)blocks > by_len) blocks = (int)by_len;
   // One chunk per CTA by default (a static partition: every chunk boundary drains and refills the rings, and
   // the measured imbalance between CTAs is smaller than that: 1M tokens on 148 SMs, chunks of 256 / 512 /
-  // 1024 tokens ran at 103 / 106 / 107 M words/s against 110 with one chunk per CTA).  MVB_WIN_CHUNK=n hands
-  // out n-token chunks dynamically instead.
+  // 1024 tokens handed out by an atomic ticket ran at 103 / 106 / 107 M words/s against 110 with one chunk per
+  // CTA).  MVB_WIN_CHUNK=n deals n-token chunks round-robin instead.
   a.chunk = (int)((h->n_tokens + blocks - 1) / blocks);
   if (const char* e = getenv("MVB_WIN_CHUNK")) {
     const int v = atoi(e);
