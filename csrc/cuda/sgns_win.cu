@@ -410,35 +410,42 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
           }
           __syncwarp();
           const int nb = (int)((nv - i0) < 32 ? (nv - i0) : 32);
-          for (int l = 0; l < nb; ++l) {
+          // four positions per pass: lane group g = lane / 8 serves position l4 + g, lane k of the group
+          // its k-th output row (kKO <= 8)
+          const int g = lane >> 3, k = lane & 7;
+          for (int l4 = 0; l4 < nb; l4 += 4) {
+            const int l = l4 + g;
+            const bool on = l < nb;
             const int64_t ii = G0 + i0 + l;                 // position in the CTA's virtual stream
             const int cw = (int)(ii % NW);
             const int64_t n = ii / NW;
             const int st = cw * 2 + (int)(n & 1);
-            mbar_wait(out_empty + st, (uint32_t)((n >> 1) & 1) ^ 1u);
-            const int act = b_act[l];
             float* optr = nullptr;
-            if (lane < kKO && act) {
-              const int r = b_rid[l * kKO + lane];
-              if (r >= 0) optr = row_of(a.out_peer, a.S, a.rps, a.ld, a.w_out, r);
+            if (on) {
+              mbar_wait(out_empty + st, (uint32_t)((n >> 1) & 1) ^ 1u);
+              const int act = b_act[l];
+              if (k < kKO && act) {
+                const int r = b_rid[l * kKO + k];
+                if (r >= 0) optr = row_of(a.out_peer, a.S, a.rps, a.ld, a.w_out, r);
+              }
+              if (k < kKO) {
+                out_meta[st].ptr[k] = optr;
+                out_meta[st].scale[k] = b_osc[l * kKO + k];
+              }
+              if (k == 0) {
+                out_meta[st].active = act;
+                out_meta[st].p = (long long)(ra - 2 * W + i0 + l);
+              }
             }
-            if (lane < kKO) {
-              out_meta[st].ptr[lane] = optr;
-              out_meta[st].scale[lane] = b_osc[l * kKO + lane];
-            }
-            if (lane == 0) {
-              out_meta[st].active = act;
-              out_meta[st].p = (long long)(ra - 2 * W + i0 + l);
-            }
-            const uint32_t have = __ballot_sync(0xffffffffu, optr != nullptr);
+            const uint32_t have = (__ballot_sync(0xffffffffu, optr != nullptr) >> (g * 8)) & 0xffu;
             __syncwarp();     // every lane's meta pointer is written before the release-arrive
-            if (lane == 0) {
+            if (on && k == 0) {
               if (have) mbar_arrive_expect_tx(out_full + st, (uint32_t)__popc(have) * (uint32_t)a.row_bytes);
               else mbar_arrive(out_full + st);
             }
             __syncwarp();     // expect_tx is armed before any copy can complete_tx
             if (optr)
-              bulk_g2s(out_rows + ((size_t)st * a.ko + lane) * a.row_bytes, optr, (uint32_t)a.row_bytes,
+              bulk_g2s(out_rows + ((size_t)st * a.ko + k) * a.row_bytes, optr, (uint32_t)a.row_bytes,
                        out_full + st);
           }
           __syncwarp();       // batch scratch is re-written next round
