@@ -412,10 +412,13 @@ sgns_win_kernel(const __grid_constant__ WinDev a) {
           const int nb = (int)((nv - i0) < 32 ? (nv - i0) : 32);
           // four positions per pass: lane group g = lane / 8 serves position l4 + g, lane k of the group
           // its k-th output row (kKO <= 8)
+          // (never two positions of the same consumer in one pass: the second one waits for a stage that is
+          // only released once the first one has been handed over)
           const int g = lane >> 3, k = lane & 7;
-          for (int l4 = 0; l4 < nb; l4 += 4) {
+          const int PW = NW < 4 ? NW : 4;
+          for (int l4 = 0; l4 < nb; l4 += PW) {
             const int l = l4 + g;
-            const bool on = l < nb;
+            const bool on = g < PW && l < nb;
             const int64_t ii = G0 + i0 + l;                 // position in the CTA's virtual stream
             const int cw = (int)(ii % NW);
             const int64_t n = ii / NW;
