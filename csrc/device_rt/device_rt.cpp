@@ -761,9 +761,22 @@ int MatrixTable<T>::AddRowsAsync(const int64_t* ids, int64_t k, const T* vals, c
     rows_->MarkStale(ids, k, this->num_row_, stream);
     return this->Record(stream);
   }
-  // collective: exchange the request sizes, publish the request in symmetric staging, owners apply
+  // collective: exchange the request sizes AND each worker's AddOption (the option travels with the request,
+  // reference: last Blob of Request_Add), publish the request in symmetric staging, owners apply
+  struct RowAddReq {
+    int64_t k;
+    MvbAddOpt opt;
+  };
+  std::vector<RowAddReq> reqs(c.size);
+  {
+    RowAddReq mine;
+    std::memset(&mine, 0, sizeof mine);
+    mine.k = k;
+    mine.opt = ToKernelOption(option, std::max(MV_WorkerId(), 0));
+    c.AllGather(&mine, sizeof mine, reqs.data());
+  }
   std::vector<int64_t> counts(c.size);
-  c.AllGather(&k, sizeof k, counts.data());
+  for (int r = 0; r < c.size; ++r) counts[r] = reqs[r].k;
   const int64_t cap = std::max<int64_t>(*std::max_element(counts.begin(), counts.end()), 1);
   if (rows_->stage_cap < cap) {
     Barrier(stream);   // nobody still reads the old staging
@@ -782,7 +795,8 @@ int MatrixTable<T>::AddRowsAsync(const int64_t* ids, int64_t k, const T* vals, c
     for (int w = 0; w < m.W; ++w) {
       const int r = MV_WorkerIdToRank(w);
       if (counts[r] == 0) continue;
-      const MvbAddOpt o = ToKernelOption(option, w);
+      MvbAddOpt o = reqs[r].opt;             // worker w's own option
+      o.worker_id = w;
       MVB_CHECK(mvb_add_rows_owner(DType<T>::code, m.upd->code, m.shard->local(), st0, st1, m.row_lo[m.sid],
                                    m.row_hi[m.sid], cols, m.state_stride,
                                    static_cast<const int64_t*>(rows_->stage_ids->peer(r)), counts[r],
