@@ -82,3 +82,65 @@ def test_gpu_c_api_library_exports_the_reference_abi():
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert set(REFERENCE_C_API) <= exported, set(REFERENCE_C_API) - exported
     assert not [n for n in exported if n.startswith("MV_") and n not in REFERENCE_C_API]
+
+
+# ---- signature-level checks (parameter count, widths and pointer-ness), still without a Lua / .NET runtime ----
+def _c_kind(t: str) -> str:
+    t = t.replace("const", " ").strip()
+    if "*" in t or "[" in t or t.split()[0] == "TableHandler":
+        return "ptr"
+    base = t.split()[0]
+    return {"int": "i32", "int64_t": "i64", "float": "f32", "double": "f64", "void": "void", "char": "i8"}[base]
+
+
+def _parse_c_decls(text: str):
+    """name -> (return kind, [parameter kinds]) for every MV_* prototype in a C declaration block."""
+    out = {}
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    for m in re.finditer(r"(?:DllExport\s+)?((?:const\s+)?\w+\s*\*?)\s*(MV_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, params = m.group(1), m.group(2), m.group(3).strip()
+        kinds = []
+        if params and params != "void":
+            for p in params.split(","):
+                p = " ".join(p.split())
+                # drop the parameter name (last identifier) unless the declarator is only a type
+                mm = re.match(r"(.*?)(\w+)(\s*\[\s*\])?$", p)
+                typ = (mm.group(1) + (mm.group(3) or "")) if mm and mm.group(1).strip() else p
+                kinds.append(_c_kind(typ))
+        out[name] = (_c_kind(ret), kinds)
+    return out
+
+
+def _header_decls():
+    return _parse_c_decls(open(os.path.join(ROOT, "include", "multiverso", "c_api.h")).read())
+
+
+def test_lua_cdef_signatures_match_the_header():
+    src = open(os.path.join(ROOT, "binding", "lua", "init.lua")).read()
+    cdef = src[src.index("ffi.cdef[[") + len("ffi.cdef[["):src.index("]]")]
+    lua, hdr = _parse_c_decls(cdef), _header_decls()
+    assert len(lua) >= len(REFERENCE_C_API)
+    for name, sig in lua.items():
+        assert hdr[name] == sig, (name, hdr[name], sig)
+
+
+_CS_KIND = {"int": "i32", "long": "i64", "float": "f32", "double": "f64", "string": "ptr", "IntPtr": "ptr",
+            "void": "void"}
+
+
+def test_csharp_pinvoke_signatures_match_the_header():
+    src = open(os.path.join(ROOT, "binding", "csharp", "MultiversoWrapper.cs")).read()
+    hdr = _header_decls()
+    decls = re.findall(r"static extern (\w+) (MV_\w+)\(([^)]*)\)", src)
+    assert len(decls) >= 15
+    for ret, name, params in decls:
+        kinds = []
+        for p in [q for q in (" ".join(x.split()) for x in params.split(",")) if q]:
+            toks = p.split()
+            typ = toks[-2]                                   # [out|ref] type name
+            by_ref = toks[0] in ("out", "ref")
+            kinds.append("ptr" if (by_ref or typ.endswith("[]")) else _CS_KIND[typ])
+        want_ret, want = hdr[name]
+        # the C string return of MV_Version is marshalled as IntPtr
+        assert _CS_KIND[ret] == want_ret, (name, ret, want_ret)
+        assert kinds == want, (name, kinds, want)
