@@ -392,7 +392,9 @@ def secondary_block(extra, world):
             "add_gbs": extra["add_gbs"], "get_gbs": extra["get_gbs"], "iters": 5,
             "config": {"table": "MatrixTable 1000000x512 fp32, whole-table Add (sgd updater fused) + whole-table Get",
                        "parallelism": f"{world} GPU(s), row-sharded, fused P2P kernels (no NCCL on the path)",
-                       "timing": "CUDA events, max over ranks; 2.05 GB table >> 126 MB L2"}}
+                       "timing": "CUDA events, max over ranks; 2.05 GB table >> 126 MB L2",
+                       "staging": "Add reads the delta from the table's zero-copy symmetric staging buffer "
+                                  "(table.staging()); an Add from an ordinary tensor pays one extra local copy"}}
 
 
 def matrix_bw_main(mv, torch, world, rank, args):
