@@ -80,17 +80,23 @@ class EventTimer {
 // collective: all ranks create and destroy their SymmBuffers in the same order.
 class SymmBuffer {
  public:
-  explicit SymmBuffer(size_t bytes);
+  // `multicast`: try to allocate through the driver's virtual memory management API and bind the slabs to an NVLS
+  // multicast object (multicast() != nullptr on success; kernels can then reduce / broadcast in the switch with
+  // multimem.ld_reduce / multimem.st).  Falls back, collectively, to the cudaIpc slabs when any rank cannot.
+  explicit SymmBuffer(size_t bytes, bool multicast = false);
   ~SymmBuffer();
   SymmBuffer(const SymmBuffer&) = delete;
   SymmBuffer& operator=(const SymmBuffer&) = delete;
   void* local() const { return ptrs_[rank_]; }
   void* peer(int rank) const { return ptrs_[rank]; }
   void* const* ptrs() const { return ptrs_; }   // void*[kMaxRanks], unused entries nullptr
+  void* multicast() const { return multicast_; }
   size_t bytes() const { return bytes_; }
 
  private:
   void* ptrs_[kMaxRanks] = {nullptr};
+  void* multicast_ = nullptr;
+  void* vmm_ = nullptr;                          // vmm::Mapping of a multicast-bound allocation
   size_t bytes_;
   int rank_;
 };

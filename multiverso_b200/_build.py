@@ -156,14 +156,18 @@ def build_device_rt(verbose: bool = False) -> Path:
     srcs = sorted(srcdir.glob("*.cpp"))
     if cxx is None or not srcs:
         return out
-    hdrs = sorted((ROOT / "include").rglob("*.h")) + [ROOT / "csrc" / "cuda" / "mvb200.h"]
+    hdrs = sorted((ROOT / "include").rglob("*.h")) + [ROOT / "csrc" / "cuda" / "mvb200.h"] + sorted(srcdir.glob("*.h"))
     inc = ["-I", str(ROOT / "include")]
+    # vmm.cpp uses the TYPES of the driver API (cuda.h); the entry points are resolved with dlopen at run time
+    nvcc = _find("nvcc", "/usr/local/cuda/bin/nvcc")
+    cuda_inc = (Path(nvcc).resolve().parent.parent / "include") if nvcc else Path("/usr/local/cuda/include")
+    lib_inc = inc + ["-I", str(cuda_inc)]
     deps = [LIBDIR / "libmultiverso.so", LIBDIR / "libmvb200.so"]
     if _newer(srcs + hdrs + deps, out):
         if verbose:
             print("[build] g++ device_rt -> libmvdevice.so", flush=True)
-        _run([cxx, *CXX_FLAGS, *inc, "-shared", *map(str, srcs), "-o", str(out), f"-L{LIBDIR}", "-lmultiverso",
-              "-lmvb200", "-Wl,-rpath,$ORIGIN"], "link libmvdevice.so")
+        _run([cxx, *CXX_FLAGS, *lib_inc, "-shared", *map(str, srcs), "-o", str(out), f"-L{LIBDIR}", "-lmultiverso",
+              "-lmvb200", "-ldl", "-Wl,-rpath,$ORIGIN"], "link libmvdevice.so")
     # the reference's C API served by the device plane (what a Lua / C# / ctypes binding can load
     # instead of libmultiverso.so to get HBM-resident tables)
     capi = sorted((srcdir / "c_api_gpu").glob("*.cpp"))
