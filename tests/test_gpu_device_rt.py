@@ -38,3 +38,16 @@ def test_cpp_device_runtime_two_gpus(sync):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", "2", "--timeout", "200", "--",
                         EXE, "all", f"-sync={sync}"], capture_output=True, text=True, timeout=260)
     assert r.returncode == 0 and r.stdout.count("PASS") == 2, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_cpp_device_runtime_nvls_aggregate_four_gpus():
+    """-device_nvls=2: the C++ runtime's large float MV_Aggregate reduces in the NVSwitch on a VMM / multicast-bound
+    staging buffer (csrc/device_rt/vmm.cpp); on a platform without multicast objects the run must still pass on
+    the two-shot fallback."""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mvrun.py"), "-n", "4", "--timeout", "200", "--",
+                        EXE, "all", "-device_nvls=2"], capture_output=True, text=True, timeout=260)
+    assert r.returncode == 0 and r.stdout.count("PASS") == 4, r.stdout[-3000:] + r.stderr[-3000:]
