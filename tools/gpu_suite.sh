@@ -149,6 +149,16 @@ bulk)
     MVB_GET_BULK=$v timeout 300 $L bench/matrix_bw.py > gpurun_out/matrix_bw_bulk$v.log 2>&1; echo "matrix_bw MVB_GET_BULK=$v rc=$?"; grep '^{' gpurun_out/matrix_bw_bulk$v.log | tail -1 | cut -c1-500
   done
   ;;
+nvls_cpp)
+  # C++ device runtime, NVLS all-reduce on VMM / multicast-bound staging (csrc/device_rt/vmm.cpp, -device_nvls):
+  # written after round 2's GPU budget was spent, NOT yet executed -- run this first (needs >= 2 GPUs; from 4 the
+  # `auto` setting 1 also takes the NVLS path).  A platform without multicast objects must pass on the fallback.
+  if [ "$NG" -gt 1 ]; then
+    for mode in 2 1; do
+      timeout 260 python tools/mvrun.py -n $NG --timeout 200 -- build/bin/mv_device_test aggregate -device_nvls=$mode > gpurun_out/devrt_nvls${mode}_n$NG.log 2>&1; echo "mv_device_test aggregate -device_nvls=$mode rc=$?"; grep -E "PASS|FAIL|EXPECT|NVLS" gpurun_out/devrt_nvls${mode}_n$NG.log | head -12
+    done
+  else echo "nvls_cpp needs > 1 GPU"; fi
+  ;;
 devrt)
   # native C++ device runtime scenarios (BSP + async) and the native GPU wordembedding application
   if [ "$NG" -gt 1 ]; then L="python tools/mvrun.py -n $NG --timeout 200 --"; else L=""; fi
