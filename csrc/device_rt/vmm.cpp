@@ -12,7 +12,10 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <vector>
+
+#include "multiverso/multiverso.h"
 
 #ifndef SYS_pidfd_open
 #define SYS_pidfd_open 434
@@ -377,4 +380,49 @@ extern "C" int mvd_vmm_available(int dev, char* why, int why_len) {
   const bool ok = multiverso::device::vmm::Available(dev, &w);
   if (why && why_len > 0) std::snprintf(why, static_cast<size_t>(why_len), "%s", w.c_str());
   return ok ? 1 : 0;
+}
+
+// Protocol self-test for the CPU box: allocate over the host control plane (MV_Init must have run), stamp the own
+// slab THROUGH A CPU POINTER, read every peer's stamp through the local mapping of its slab, write through the
+// multicast view, release.  Only meaningful against the driver test double (tests/fake_libcuda.c), where a "slab"
+// is host memory; with a real driver the pointers are device addresses and this function must not be called.
+// Returns 1 = allocated and verified, 0 = collectively fell back (msg = why), -1 = verification failed.
+extern "C" int mvd_vmm_selftest_hostmapped(long long bytes, char* msg, int msg_len) {
+  namespace vmm = multiverso::device::vmm;
+  const int rank = multiverso::MV_Rank(), world = multiverso::MV_Size();
+  const vmm::AllGatherFn gather = [rank, world](const void* mine, size_t n, void* all) {
+    std::memset(all, 0, n * static_cast<size_t>(world));
+    std::memcpy(static_cast<char*>(all) + n * static_cast<size_t>(rank), mine, n);
+    if (world > 1) multiverso::MV_Aggregate(static_cast<char*>(all), static_cast<int>(n * static_cast<size_t>(world)));
+  };
+  auto say = [&](const std::string& m) {
+    if (msg && msg_len > 0) std::snprintf(msg, static_cast<size_t>(msg_len), "%s", m.c_str());
+  };
+  vmm::Mapping m;
+  std::string why;
+  if (!vmm::Allocate(static_cast<size_t>(bytes), rank, world, 0, gather, &m, &why)) {
+    say(why);
+    return 0;
+  }
+  auto rendezvous = [&] {
+    char one = 1;
+    std::vector<char> all(static_cast<size_t>(world));
+    gather(&one, 1, all.data());
+  };
+  bool ok = m.size >= static_cast<size_t>(bytes) && m.multicast != nullptr;
+  const size_t words = m.size / 4;
+  auto* mine = static_cast<volatile uint32_t*>(m.ptrs[rank]);
+  mine[0] = 0xC0DE0000u + static_cast<uint32_t>(rank);
+  mine[words - 1] = 0xFEED0000u + static_cast<uint32_t>(rank);
+  if (rank == 0) static_cast<volatile uint32_t*>(m.multicast)[1] = 0xABCD1234u;
+  rendezvous();
+  for (int r = 0; r < world; ++r) {
+    auto* p = static_cast<volatile uint32_t*>(m.ptrs[r]);
+    ok = ok && p != nullptr && p[0] == 0xC0DE0000u + static_cast<uint32_t>(r) && p[words - 1] == 0xFEED0000u + static_cast<uint32_t>(r);
+  }
+  ok = ok && static_cast<volatile uint32_t*>(m.multicast)[1] == 0xABCD1234u;
+  rendezvous();
+  vmm::Release(&m, gather);
+  say(ok ? "ok" : "a peer's slab did not show its stamp through the local mapping");
+  return ok ? 1 : -1;
 }

@@ -63,6 +63,7 @@ extern "C" {
 int mvd_dup_fd_from_pid(int pid, int fd);
 void mvd_allow_fd_duplication(void);
 int mvd_vmm_available(int dev, char* why, int why_len);
+int mvd_vmm_selftest_hostmapped(long long bytes, char* msg, int msg_len);   /* test double only, see vmm.cpp */
 }
 
 #endif  // MULTIVERSO_DEVICE_RT_VMM_H_
